@@ -1,0 +1,87 @@
+"""Parity cases shared by tests/golden/make_golden.py (which runs the REFERENCE on
+them in the build container) and by the tests (which run the oracle / the CUDA
+path on the same inputs and compare with the committed outputs)."""
+
+from pathlib import Path
+
+import numpy as np
+
+from sykepic_b200 import synth
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+FIXTURE = GOLDEN / "ref_fixture"
+VALID_BIN = "D20180712T065600_IFCB114"
+
+def edge_bin(seed):
+    """Small bin exercising every branch of the decode / transform."""
+    rng = np.random.default_rng(seed)
+    shapes = [
+        (0, 0),  # empty row (ROI id skipped)
+        (56, 42), (128, 53),  # the reference fixture's geometry
+        (360, 100), (448, 224), (448, 100),  # exact 2x of T=180 / T=224 (INTER_AREA switch) and near miss
+        (180, 70), (224, 224), (180, 180), (224, 88),  # identity width
+        (24, 120), (50, 51), (51, 50), (64, 64),  # h > w, near-square, square
+        (16, 8), (35, 18), (1, 1), (2, 1), (1, 2), (3, 180), (180, 3),
+        (0, 7),  # width 0, height 7: skipped
+        (956, 394), (1380, 1034), (1376, 8),  # real max, clip max, extreme aspect (still >= 1 px at T=180)
+        (88, 50), (96, 48), (104, 52), (72, 40), (200, 114),
+    ]
+    w = np.array([s[0] for s in shapes], np.int32)
+    h = np.array([s[1] for s in shapes], np.int32)
+    area = w.astype(np.int64) * h
+    start = np.concatenate([[0], np.cumsum(area)[:-1]]).astype(np.int64)
+    roi = np.empty(int(area.sum()), np.uint8)
+    for i in range(len(shapes)):
+        if not area[i]:
+            continue
+        if i % 3 == 0:
+            px = rng.integers(0, 256, (h[i], w[i]), dtype=np.uint8)  # uniform: mode ties likely
+        elif i % 3 == 1:
+            px = (rng.integers(0, 3, (h[i], w[i])) * 100 + 17).astype(np.uint8)  # 3 levels: big ties
+        else:
+            px = synth.synth_roi_pixels(rng, int(w[i]), int(h[i]))
+        roi[start[i] : start[i] + area[i]] = px.ravel()
+    return {"adc_text": synth.adc_text(w, h, start, rng), "roi_bytes": roi, "w": w, "h": h, "start": start}
+
+
+
+
+LOGIT_GAIN = 24.0
+
+CASES = {
+    # the reference's test configuration: ResNet-18, 3x180x180, mode border, no normalisation
+    "r18_180": dict(arch="resnet18", t=180, border="mode", norm=False, seed=0, tap_limit=64,
+                    bins=[(VALID_BIN, "valid"), (synth.bin_name(0), ("edge", 7)), (synth.bin_name(1), ("synth", 1001, 40, False))]),
+    # benchmark configuration 2 geometry with ImageNet normalisation and a white border
+    "r18_224n": dict(arch="resnet18", t=224, border="white", norm=True, seed=1, tap_limit=8,
+                     bins=[(synth.bin_name(2), ("edge", 8)), (synth.bin_name(3), ("synth", 1003, 24, True))]),
+    # ResNet-50 (bottleneck blocks), black border
+    "r50_224": dict(arch="resnet50", t=224, border="black", norm=False, seed=2, tap_limit=4,
+                    bins=[(synth.bin_name(4), ("synth", 1004, 24, False))]),
+}
+
+
+def make_bin(spec):
+    if spec == "valid":
+        return {"adc_text": (FIXTURE / f"{VALID_BIN}.adc").read_bytes().decode(),
+                "roi_bytes": np.fromfile(FIXTURE / f"{VALID_BIN}.roi", np.uint8)}
+    if spec[0] == "edge":
+        return edge_bin(spec[1])
+    return synth.synth_bin(spec[1], spec[2], uniform_pixels=spec[3])
+
+
+def case_bins(name):
+    return [(bname, make_bin(spec)) for bname, spec in CASES[name]["bins"]]
+
+
+def fixture_classes():
+    return (FIXTURE / "class_names.txt").read_text().splitlines()
+
+
+def case_model_dir(name, root):
+    """Model dir (config.ini, class_names.txt, best_state.pth) identical to the one the goldens were made with."""
+    c = CASES[name]
+    stats = dict(np.load(GOLDEN / f"calib_{name}.npz"))
+    return synth.write_model_dir(Path(root) / f"model_{name}", arch=c["arch"], t=c["t"], head=(256, 128), seed=c["seed"],
+                                 border=c["border"], imagenet_normalization=c["norm"], classes=fixture_classes(),
+                                 logit_gain=LOGIT_GAIN, bn_stats=stats)

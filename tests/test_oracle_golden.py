@@ -1,0 +1,138 @@
+"""The oracle (numpy / torch-CPU restatement) against what the REFERENCE produced.
+
+Goldens: tests/golden/* (made by tests/golden/make_golden.py, which runs the
+reference's own code) and the reference's own fixtures (ref_fixture/).
+"""
+
+import hashlib
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ifcb, network, pipeline, prediction, preprocess
+from tests.cases import CASES, FIXTURE, GOLDEN, VALID_BIN, case_bins
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+ALL_BINS = [(c, i) for c in CASES for i in range(len(CASES[c]["bins"]))]
+
+
+@pytest.fixture(scope="module")
+def bins():
+    return {c: case_bins(c) for c in CASES}
+
+
+@pytest.mark.parametrize("case,idx", ALL_BINS)
+def test_generated_bins_are_the_golden_bins(bins, case, idx):
+    bname, b = bins[case][idx]
+    g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+    assert sha(b["roi_bytes"]) == str(g["roi_bytes_sha"])
+    assert hashlib.sha256(b["adc_text"].encode()).hexdigest() == str(g["adc_sha"])
+
+
+@pytest.mark.parametrize("case,idx", ALL_BINS)
+def test_decode_bit_exact(bins, case, idx):
+    bname, b = bins[case][idx]
+    g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+    rows = ifcb.parse_adc_text(b["adc_text"])
+    assert [r[0] for r in rows] == g["roi_id"].tolist()
+    assert [r[1] for r in rows] == g["w"].tolist()
+    assert [r[2] for r in rows] == g["h"].tolist()
+    for (rid, img), want in zip(ifcb.decode_rois(rows, b["roi_bytes"]), g["roi_sha"]):
+        assert sha(img) == str(want), rid
+
+
+def test_reference_fixture_geometry():
+    """ROI 1 is 0x0 and skipped; 56x42 @0 and 128x53 @2352."""
+    rows = ifcb.parse_adc(FIXTURE / f"{VALID_BIN}.adc")
+    assert rows == [(2, 56, 42, 0), (3, 128, 53, 2352)]
+
+
+@pytest.mark.parametrize("case,idx", ALL_BINS)
+def test_preprocess_bit_exact(bins, case, idx):
+    c = CASES[case]
+    bname, b = bins[case][idx]
+    g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+    rows = ifcb.parse_adc_text(b["adc_text"])
+    for k, (rid, img) in enumerate(ifcb.decode_rois(rows, b["roi_bytes"])):
+        if k < len(g["u8_taps"]):
+            got = preprocess.resize_with_border_u8(img, c["t"], c["t"], c["border"])
+            assert np.array_equal(got, g["u8_taps"][k]), (rid, img.shape)
+        # config.py:55-56: `imagenet_normalization` only reaches the TRAIN transform
+        x = preprocess.eval_transform(img, c["t"], c["t"], c["border"], False)
+        assert sha(x) == str(g["f32_sha"][k]), (rid, img.shape)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_network_and_csv(bins, model_dirs, case):
+    model = pipeline.prepare_model(model_dirs(case))
+    torch.set_num_threads(8)
+    for bname, b in bins[case]:
+        g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+        rows = ifcb.parse_adc_text(b["adc_text"])
+        imgs = [img for _, img in ifcb.decode_rois(rows, b["roi_bytes"])]
+        x = torch.from_numpy(pipeline.preprocess_rois(model, imgs))
+        logits = network.forward_logits(model.state_dict, x)
+        scale = max(1.0, float(np.abs(g["logits"]).max()))
+        assert np.abs(logits.numpy() - g["logits"]).max() <= 2e-5 * scale
+        probs = network.probabilities(logits).numpy()
+        assert np.abs(probs - g["probs"]).max() <= 1e-5
+        text = pipeline.prediction.probabilities_to_csv_text(
+            pipeline.net_pass(model, rows, b["roi_bytes"], batch_size=16), model.classes)
+        want = (GOLDEN / f"case_{case}__{bname}.prob.csv").read_text()
+        cls_a, ids_a, val_a = prediction.parse_prob_csv_text(text)
+        cls_b, ids_b, val_b = prediction.parse_prob_csv_text(want)
+        assert cls_a == cls_b and ids_a.tolist() == ids_b.tolist()
+        assert np.abs(val_a - val_b).max() <= 2e-5  # at most one unit of the 5th decimal
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_labels_and_counts(case):
+    labels = json.loads((GOLDEN / f"case_{case}.labels.json").read_text())
+    for bname, lab in labels.items():
+        classes, ids, vals = prediction.parse_prob_csv_text((GOLDEN / f"case_{case}__{bname}.prob.csv").read_text())
+        for tname in ("thresholds-2021", "thresholds-zero", "scalar-0.5"):
+            thr = 0.5 if tname.startswith("scalar") else prediction.threshold_dictionary(FIXTURE / f"{tname}.txt")
+            names, flags = prediction.predict(vals, classes, thr)
+            assert names == lab[tname]["prediction"], (bname, tname)
+            assert flags.tolist() == lab[tname]["classified"], (bname, tname)
+            if "counts" in lab[tname]:
+                assert prediction.class_counts_probs_only(vals, classes, thr) == lab[tname]["counts"]
+
+
+def test_reference_own_golden_csv_labels():
+    """zero thresholds => ROI 2 Uroglenopsis_sp, ROI 3 Licmophora_sp, both classified;
+    2021 thresholds => neither classified; counts 1/1/2 (tests/test_classification.py:61-65)."""
+    real = json.loads((GOLDEN / "ref_fixture_labels.json").read_text())
+    classes, ids, vals = prediction.parse_prob_csv_text((FIXTURE / f"{VALID_BIN}.prob.csv").read_text())
+    assert ids.tolist() == [2, 3] and len(classes) == 50
+    for tname, want in real.items():
+        thr = prediction.threshold_dictionary(FIXTURE / f"{tname}.txt")
+        names, flags = prediction.predict(vals, classes, thr)
+        assert names == want["prediction"] and flags.tolist() == want["classified"]
+        assert prediction.class_counts_probs_only(vals, classes, thr) == want["counts"]
+    names, flags = prediction.predict(vals, classes, prediction.threshold_dictionary(FIXTURE / "thresholds-zero.txt"))
+    assert names == ["Uroglenopsis_sp", "Licmophora_sp"] and flags.all()
+    counts = prediction.class_counts_probs_only(vals, classes, prediction.threshold_dictionary(FIXTURE / "thresholds-zero.txt"))
+    assert counts["Uroglenopsis_sp"] == 1 and counts["Licmophora_sp"] == 1 and counts["Total"] == 2
+
+
+def test_truncated_roi_is_faulty():
+    """probability.py:111-112: a slice shorter than w*h raises ValueError."""
+    rows = ifcb.parse_adc(FIXTURE / f"{VALID_BIN}.adc")
+    data = np.fromfile(FIXTURE / f"{VALID_BIN}.roi", np.uint8)
+    with pytest.raises(ValueError):
+        list(ifcb.decode_rois(rows, data[:-1]))
+    geo = np.load(GOLDEN / "invalid_adc_geometry.npz")["whs"]
+    assert len(geo) == 4613 and (geo[:, 0] < 1).sum() == 2
+
+
+def test_csv_path_layout():
+    assert str(ifcb.sample_csv_path("/x/y/D20180712T065600_IFCB114", "/out", ".prob")) == \
+        "/out/2018/07/12/D20180712T065600_IFCB114.prob.csv"
+    assert ifcb.sample_to_datetime("D20180712T065600_IFCB114", True) == "2018-07-12T06:56:00+00:00"
