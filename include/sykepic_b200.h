@@ -1,0 +1,190 @@
+/*
+ * sykepic_b200 -- C ABI of the B200-native `sykepic prob` / `sykepic class` hot path.
+ *
+ * The reference (sykefi/syke-pic) is pure Python and has NO FFI / plugin interface
+ * (SURVEY.md section 8b); its boundary for this path is a set of Python call
+ * signatures.  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch/Python types.
+ *   - Every function returns an int status: 0 = SPK_OK, negative = error.
+ *     `spk_last_error(ctx)` gives a human-readable message for the last failure on
+ *     that context (or the last context-free failure of the calling thread when
+ *     ctx == NULL).
+ *   - The CALLER owns every buffer it passes (device pointers from e.g.
+ *     torch.Tensor.data_ptr(), pinned host buffers).  The library owns only what
+ *     hangs off the opaque `spk_ctx` (packed/folded weights, activation workspace,
+ *     TMA descriptors) created by spk_create and freed by spk_destroy.
+ *   - All device work is enqueued asynchronously on the context's CUDA stream
+ *     (spk_create / spk_set_stream); nothing synchronises unless stated.
+ *   - One context is used by one host thread at a time (one process per GPU).
+ */
+#ifndef SYKEPIC_B200_H
+#define SYKEPIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPK_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define SPK_OK                 0
+#define SPK_ERR_INVALID       -1  /* bad argument */
+#define SPK_ERR_CUDA          -2  /* CUDA runtime / driver error (message has the detail) */
+#define SPK_ERR_FAULTY_BIN    -3  /* ROI slice runs past the .roi bytes: the reference's ValueError
+                                     "Faulty raw data" (sykepic/compute/probability.py:111-112); skip the bin */
+#define SPK_ERR_EMPTY_RESIZE  -4  /* aspect ratio > T:1 gives a 0-pixel side: cv2.error in the reference,
+                                     bin skipped (probability.py:113-114) */
+#define SPK_ERR_PARSE         -5  /* malformed .adc line (reference: IndexError / ValueError -> bin skipped) */
+#define SPK_ERR_CAPACITY      -6  /* caller-provided output buffer too small */
+#define SPK_ERR_UNSUPPORTED   -7
+#define SPK_ERR_STATE         -8  /* call order violated (e.g. spk_forward before spk_net_end) */
+
+/* ---- enums -------------------------------------------------------------------------- */
+enum { SPK_BORDER_MODE = 0, SPK_BORDER_BLACK = 1, SPK_BORDER_WHITE = 2 }; /* sykepic/train/image.py:20-28 */
+enum { SPK_DTYPE_F32 = 0, SPK_DTYPE_BF16 = 1, SPK_DTYPE_U8 = 2 };
+enum { SPK_LAYOUT_NCHW = 0, SPK_LAYOUT_NHWC = 1 };
+enum { SPK_PRECISION_FP32 = 0, SPK_PRECISION_BF16 = 1 };
+/* implementation selector for convolutions in bf16 precision */
+enum { SPK_CONV_AUTO = 0, SPK_CONV_SIMT = 1, SPK_CONV_TCGEN05 = 2 };
+
+typedef struct spk_ctx spk_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int spk_abi_version(void);
+/* stream: a cudaStream_t (NULL = the legacy default stream). */
+int spk_create(int device, void* stream, spk_ctx** out);
+int spk_destroy(spk_ctx* ctx);
+int spk_set_stream(spk_ctx* ctx, void* stream);
+int spk_synchronize(spk_ctx* ctx);
+const char* spk_last_error(const spk_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t spk_launch_count(const spk_ctx* ctx);
+
+/* ---- A2: .adc parsing (host) ---------------------------------------------------------
+ * Replaces the per-line parsing in sykepic/utils/ifcb.py:101-110 (raw_to_png) and
+ * :133-145 (next_roi): ROI id = 1-based LINE number, width/height/start = comma fields
+ * 15/16/17 with Python int() syntax (optional whitespace and sign), rows with
+ * width < 1 or height < 1 skipped.  Universal newlines (\n, \r\n, \r).
+ * Outputs hold the non-empty ROIs in file order; *n_out their count, *n_lines the
+ * number of lines seen.  SPK_ERR_PARSE on a short / non-integer line (the reference
+ * raises and the bin is skipped), SPK_ERR_CAPACITY when cap is too small. */
+int spk_adc_parse(const char* text, int64_t len, int64_t cap,
+                  int32_t* roi_id, int32_t* width, int32_t* height, int64_t* start,
+                  int64_t* n_out, int64_t* n_lines);
+
+/* Geometry checks the reference performs implicitly while decoding / resizing one bin:
+ * start + w*h <= roi_len for every ROI (else SPK_ERR_FAULTY_BIN, ifcb.py:111-116 reshape)
+ * and both resized sides >= 1 px for the target (else SPK_ERR_EMPTY_RESIZE,
+ * sykepic/train/image.py:183-198 + cv2.resize).  *first_bad = index of the first
+ * offending ROI (or -1). */
+int spk_rois_validate(const int32_t* width, const int32_t* height, const int64_t* start, int64_t n,
+                      int64_t roi_len, int target_h, int target_w, int64_t* first_bad);
+
+/* get_new_dims of sykepic/train/image.py:183-198 (float64 arithmetic, truncation). */
+void spk_new_dims(int h, int w, int target_h, int target_w, int* new_h, int* new_w);
+
+/* ---- A2+A3+A4+A5(loader): ROI decode + eval transform (device, kernel K1) -------------
+ * Replaces ifcb.raw_to_png (utils/ifcb.py:76-118) + ImageDataset.__getitem__
+ * (train/data.py:210-231) + Compose.__call__ (train/image.py:25-56: mode border,
+ * get_new_dims, cv2 INTER_LINEAR fixed-point resize incl. the 2x INTER_AREA switch and
+ * the identity copy, centred copyMakeBorder) + ToTensor (+ optional Normalize through
+ * the LUT) + default collate, for a batch of n ROIs.
+ *   roi_bytes   device, the raw .roi byte stream of the bin (roi_len bytes)
+ *   start/w/h   device, per-ROI start byte (int64), width, height (int32)
+ *   channels    1 or 3 (3 = identical planes unless the LUT differs per channel)
+ *   out_dtype   SPK_DTYPE_F32 / SPK_DTYPE_BF16 (LUT applied) or SPK_DTYPE_U8 (the
+ *               resized + padded bytes, no LUT, channels must be 1)
+ *   lut         device float[3*256] or NULL (NULL = ToTensor's v/255 for every channel)
+ *   out         device, [n, channels, T_h, T_w] (NCHW) or [n, T_h, T_w, channels] (NHWC)
+ * ROIs whose geometry is invalid (see spk_rois_validate) are filled with the border
+ * value / zero and counted in the context's device-side fault counter, which
+ * spk_fault_count reads back (synchronises). */
+int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t roi_len,
+                   const int64_t* start, const int32_t* width, const int32_t* height, int64_t n,
+                   int target_h, int target_w, int border_mode, int channels,
+                   int out_dtype, int out_layout, const float* lut, void* out);
+int spk_fault_count(spk_ctx* ctx, int64_t* count);
+
+/* ---- A5/A6/A7: the network (kernels K2) -----------------------------------------------
+ * Replaces prepare_model's get_network + load_state_dict (compute/probability.py:118-130,
+ * train/config.py:63-77, train/network.py:14-64) and TorchVisionNet.forward's `base`
+ * (train/network.py:66-68).  The host walks the state_dict (the checkpoint format is
+ * kept) and describes the graph op by op; the library folds eval-mode BatchNorm into
+ * the convolution (w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps), in double),
+ * packs weights for its kernels and plans the activation workspace.
+ * Activations are NHWC.  Buffer ids are small integers chosen by the caller;
+ * buffer 0 is the network input (the preprocessed batch, set at spk_forward). */
+int spk_net_begin(spk_ctx* ctx, int target_h, int target_w, int in_channels, int precision, int max_batch);
+/* Declare activation buffer `buf` (NHWC, `channels` wide).  Optional for buffers a single op writes
+ * completely (their shape is inferred); required for concatenation buffers that several convolutions
+ * fill slice by slice (DenseNet blocks, torch.cat in torchvision's _DenseLayer). */
+int spk_net_buffer(spk_ctx* ctx, int buf, int h, int w, int channels);
+/* weight: host float[cout*cin*kh*kw] (OIHW, as in the state_dict); bn_*: host float[cout] or NULL;
+ * bias: host float[cout] or NULL; res_buf: buffer added before the ReLU, or -1.
+ * The convolution reads channels [in_c_off, in_c_off+cin) of in_buf and writes channels
+ * [out_c_off, out_c_off+cout) of out_buf.
+ * When cin is 3 and the network input has 1 channel (identical planes), the three
+ * input-channel slices are summed (exact fold of R=G=B). */
+int spk_net_conv(spk_ctx* ctx, int in_buf, int in_c_off, int out_buf, int out_c_off, int res_buf,
+                 const float* weight, int cout, int cin, int kh, int kw, int stride, int pad,
+                 const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
+                 const float* bias, int relu, int impl);
+int spk_net_maxpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride, int pad);
+/* k x k / stride average pool, no padding (DenseNet transition). */
+int spk_net_avgpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride);
+/* Eval-mode BatchNorm (+ ReLU) as a stand-alone op on channels [0, channels) of in_buf: DenseNet's
+ * pre-activation norm1 / transition norm / norm5, which cannot be folded into the producer. */
+int spk_net_bn_relu(spk_ctx* ctx, int in_buf, int out_buf, int channels,
+                    const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
+                    int relu);
+/* Global average pool of `in_buf` followed by the all-Linear head (train/network.py:56-63,
+ * 68-69; no activations, Dropout = identity in eval).  weights[i]: host float[dims[i+1]*dims[i]],
+ * biases[i]: host float[dims[i+1]].  The chain is folded into one affine map in double. */
+int spk_net_head(spk_ctx* ctx, int in_buf, int n_layers, const float* const* weights,
+                 const float* const* biases, const int* dims);
+int spk_net_end(spk_ctx* ctx);
+/* Bytes of device memory the network holds (weights + workspace). */
+int64_t spk_net_bytes(const spk_ctx* ctx);
+
+/* ---- A6/A8/A10: forward + softmax + per-class threshold (kernels K2, K3) ---------------
+ * Replaces net_pass (compute/probability.py:180-197: logits * ln(1.3) in fp32, softmax)
+ * and, fused, prediction.row_prediction (compute/prediction.py:49-71) evaluated on the
+ * 5-decimal values the CSV would hold.
+ *   x            device, preprocessed batch in the layout spk_net_begin implies:
+ *                [n, T, T] u8 (bf16 precision, 1 channel) or [n, T, T, C] f32 NHWC
+ *   softmax_scale  ln(1.3) in the reference (probability.py:18,192-193); 0 = plain softmax
+ *   thr_q        device int32[K] or NULL: per class, the smallest value of
+ *                round(p * 1e5) that counts as "above threshold" (INT32_MAX = class has
+ *                no threshold); see spk_threshold_quantize.
+ *   probs        device float[n*K]
+ *   label        device int32[n] or NULL, classified device uint8[n] or NULL
+ */
+int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, const int32_t* thr_q,
+                float* probs, int32_t* label, uint8_t* classified);
+/* Logits of the last spk_forward (device float[n*K], owned by the context). */
+const float* spk_last_logits(const spk_ctx* ctx);
+/* Debug / test tap: copy activation buffer `buf` of the last forward to host as fp32 NHWC. */
+int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64_t cap_elems, int* h, int* w, int* c);
+
+/* Host: turn a decimal threshold into the integer domain of round(p*1e5):
+ * strict = 0: smallest q with (double)(q/1e5 as parsed from "%.5f") >= thr   (dict thresholds, prediction.py:63-64)
+ * strict = 1: smallest q with value > thr                                    (scalar threshold, prediction.py:58-59) */
+int32_t spk_threshold_quantize(double thr, int strict);
+
+/* ---- A9: .prob.csv formatting (host) ----------------------------------------------------
+ * Replaces probabilities_to_csv (compute/probability.py:200-206): header line, then per
+ * ROI "<id>,<p:.5f>,...\n" with p widened to double and correctly rounded.
+ * Writes at most cap bytes into out, *len = bytes needed. */
+int spk_format_prob_csv(const char* header_line, const int32_t* roi_id, const float* probs,
+                        int64_t n, int k, char* out, int64_t cap, int64_t* len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYKEPIC_B200_H */

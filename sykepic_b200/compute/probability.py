@@ -1,0 +1,264 @@
+"""Compute class probabilities for raw IFCB data on B200 GPUs.
+
+Drop-in for the reference's `sykepic.compute.probability` (file:line below are the
+reference's): same entry points, argument meaning, CSV layout, skip / --force
+behaviour and per-bin error handling, but no PNG round trip, no DataLoader workers
+and no PyTorch execution -- each bin is decoded, transformed and classified by the
+CUDA library (sykepic_b200/csrc) through its C ABI.
+
+  call                  probability.py:27-64
+  main                  probability.py:67-115   (returns the set of processed samples)
+  prepare_model         probability.py:118-130
+  process_sample        probability.py:133-162
+  process_images        probability.py:165-177
+  net_pass              probability.py:180-197
+  probabilities_to_csv  probability.py:200-206
+
+Extensions (keyword-only, defaults keep the reference's behaviour): `precision`
+("fp32" | "bf16") and `devices` (GPU ids; bins are sharded over them, one engine
+and one host thread per GPU, no collective -- SURVEY.md 8e).
+"""
+
+import os
+import threading
+from collections import namedtuple
+from pathlib import Path
+
+import numpy as np
+
+from .. import engine as _engine
+from .. import shard
+from ..utils import files, ifcb, logger
+
+SOFTMAX_EXP = _engine.SOFTMAX_EXP
+FILE_SUFFIX = ".prob"
+log = logger.get_logger("prob")
+EvalParams = namedtuple(
+    "EvalParams",
+    ["batch_size", "num_workers", "classes", "img_shape", "transform", "device"],
+)
+DEFAULT_PRECISION = os.environ.get("SYKEPIC_PRECISION", "fp32")
+
+
+def call(args):
+    """Entry point of `sykepic prob` (argparse namespace, or any object with the same attributes)."""
+    if getattr(args, "image_dir", None) or getattr(args, "images", None):
+        samples_as_images = True
+        if args.image_dir:
+            img_paths = sorted(Path(args.image_dir).rglob("*.png"))
+        else:
+            img_paths = sorted(Path(path) for path in args.images)
+        sample_paths = {}
+        for img_path in img_paths:
+            sample_paths.setdefault(img_path.name.rpartition("_")[0], []).append(img_path)
+        filtered = sample_paths
+    else:
+        samples_as_images = False
+        if getattr(args, "raw", None):
+            sample_paths = files.list_sample_paths(args.raw)
+        else:
+            sample_paths = [Path(path) for path in args.samples]
+        # bins whose .roi is over 1 GB are not processed (probability.py:45-51)
+        filtered = []
+        for sample_path in sample_paths:
+            if sample_path.with_suffix(".roi").stat().st_size <= 1e9:
+                filtered.append(sample_path)
+            else:
+                log.warning(f"{sample_path.name} is over 1G, skipping")
+    return main(
+        filtered,
+        args.model,
+        args.out,
+        args.batch_size,
+        args.num_workers,
+        args.force,
+        progress_bar=True,
+        samples_as_images=samples_as_images,
+        precision=getattr(args, "precision", None),
+        devices=getattr(args, "devices", None),
+    )
+
+
+def _devices(devices):
+    import torch
+
+    if devices is None:
+        env = os.environ.get("SYKEPIC_DEVICES")
+        if env:
+            devices = [int(d) for d in env.split(",") if d.strip()]
+        else:
+            devices = [int(os.environ.get("LOCAL_RANK", 0))] if torch.cuda.is_available() else [0]
+    elif isinstance(devices, int):
+        devices = list(range(devices))
+    return list(devices)
+
+
+def main(
+    sample_paths,
+    model_dir,
+    out_dir,
+    batch_size=64,
+    num_workers=2,
+    force=False,
+    progress_bar=True,
+    samples_as_images=False,
+    *,
+    precision=None,
+    devices=None,
+):
+    """`num_workers` is accepted for compatibility; there are no loader processes here."""
+    devices = _devices(devices)
+    precision = precision or DEFAULT_PRECISION
+    spec = _engine.ModelSpec.from_dir(model_dir)
+    max_batch = max(int(batch_size), 1)
+
+    def make_params(dev):
+        net = _engine.Engine(spec, device=dev, precision=precision, max_batch=max_batch)
+        return net, EvalParams(batch_size=batch_size, num_workers=num_workers, classes=spec.classes,
+                               img_shape=spec.img_shape, transform=None, device=net.device)
+
+    if samples_as_images:
+        net, params = make_params(devices[0])
+        items = list(sample_paths.items())
+        for sample, img_paths in _progress(items, progress_bar):
+            csv_path = Path(out_dir) / f"{sample}{FILE_SUFFIX}.csv"
+            process_images(img_paths, net, params, csv_path, force)
+        return None
+
+    sample_paths = list(sample_paths)
+    samples_processed = set()
+    if len(devices) <= 1:
+        net, params = make_params(devices[0])
+        for sample_path in _progress(sample_paths, progress_bar):
+            _guarded(sample_path, net, params, out_dir, force, samples_processed)
+        return samples_processed
+
+    # ---- bins sharded over the GPUs of the box; host-side merge = union of the per-GPU sets
+    shards = shard.assign_bins(sample_paths, len(devices))
+    results = [set() for _ in devices]
+    errors = []
+
+    def worker(i):
+        try:
+            net, params = make_params(devices[i])
+            for sample_path in shards[i]:
+                _guarded(sample_path, net, params, out_dir, force, results[i])
+        except Exception as e:  # engine construction failed: report, do not hang the others
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,), name=f"spk-gpu{devices[i]}") for i in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    for r in results:
+        samples_processed |= r
+    return samples_processed
+
+
+def _progress(items, progress_bar):
+    if not progress_bar:
+        return items
+    try:
+        from tqdm import tqdm
+    except ImportError:
+        return items
+    return tqdm(items, desc="Processing samples")
+
+
+def _guarded(sample_path, net, params, out_dir, force, processed):
+    """Per-bin error policy of the reference (probability.py:106-114): log and carry on."""
+    sample_path = Path(sample_path)
+    try:
+        processed.add(process_sample(sample_path, net, params, out_dir, force))
+    except ValueError:
+        log.exception(f"Faulty raw data for {sample_path.name}")
+    except Exception:
+        log.exception(f"Unexpected error for {sample_path.name}:")
+
+
+def prepare_model(model_dir, precision=None, device=None, max_batch=256):
+    """-> (net, classes, img_shape, eval_transform, device) like the reference; `net` is an Engine,
+    the eval transform is part of it (K1) and reported as None."""
+    devs = _devices(None if device is None else [device])
+    net = _engine.Engine(model_dir, device=devs[0], precision=precision or DEFAULT_PRECISION, max_batch=max_batch)
+    return net, net.spec.classes, net.spec.img_shape, None, net.device
+
+
+def process_sample(sample_path, net, params, out_dir, force=False):
+    sample_path = Path(sample_path)
+    sample = sample_path.name
+    csv_path = files.sample_csv_path(sample_path, out_dir, suffix=FILE_SUFFIX)
+    if csv_path.is_file():
+        if force:
+            log.warning(f"{csv_path.name} already exists, overwriting")
+        else:
+            log.warning(f"{csv_path.name} already exists, skipping")
+            return sample
+    log.debug(f"Computing probabilities for {sample}")
+    # appending the suffix (not with_suffix) would be the literal mirror; bin names have no dots
+    with open(sample_path.with_suffix(".adc"), "rb") as fh:
+        adc = fh.read()
+    roi = np.fromfile(sample_path.with_suffix(".roi"), dtype=np.uint8)
+    roi_id, probs = net.run_bin(adc, roi, batch_size=params.batch_size)
+    _write_csv(roi_id, probs, params.classes, csv_path)
+    return sample
+
+
+def process_images(img_paths, net, params, csv_path, force=False):
+    """`--image-dir` / `--images` mode: ROIs come from PNG files named <sample>_<roi>.png
+    (probability.py:165-177, :190).  The PNGs are decoded on the host (gray, as cv2.imread's three
+    equal planes) and packed into one byte stream, then take the same device path as a raw bin."""
+    csv_path = Path(csv_path)
+    if csv_path.is_file():
+        if force:
+            log.warning(f"{csv_path.name} already exists, overwriting")
+        else:
+            log.warning(f"{csv_path.name} already exists, skipping")
+            return
+    from .. import png
+
+    rois, ids = [], []
+    for p in img_paths:
+        img = png.read_gray(p)
+        rois.append(img)
+        ids.append(int(Path(p).stem.split("_")[-1]))
+    probabilities = net_pass(net, list(zip(ids, rois)), batch_size=params.batch_size)
+    probabilities_to_csv(probabilities, params.classes, csv_path)
+
+
+def net_pass(net, rois, device=None, batch_size=None):
+    """[(roi_id, (h,w) uint8 array), ...] -> [(roi_id, [p, ...]), ...] sorted by ROI id
+    (probability.py:180-197; the reference takes a DataLoader over PNG files here)."""
+    rois = list(rois)
+    if not rois:
+        return []
+    w = np.array([r.shape[1] for _, r in rois], np.int32)
+    h = np.array([r.shape[0] for _, r in rois], np.int32)
+    area = w.astype(np.int64) * h
+    start = np.concatenate([[0], np.cumsum(area)[:-1]]).astype(np.int64)
+    data = np.concatenate([np.ascontiguousarray(r, dtype=np.uint8).ravel() for _, r in rois])
+    ids = np.array([i for i, _ in rois], np.int32)
+    probs = net.run_rois(ids, w, h, start, data, batch_size=batch_size)
+    return sorted(zip(ids.tolist(), probs.tolist()))
+
+
+def probabilities_to_csv(probabilities, classes, csv_path):
+    """[(roi, [p...]), ...] -> csv_path; header `roi,<classes>`, `%.5f` values (probability.py:200-206)."""
+    probabilities = list(probabilities)
+    roi_id = np.array([r for r, _ in probabilities], np.int32)
+    probs = np.array([p for _, p in probabilities], np.float32).reshape(len(probabilities), len(classes))
+    _write_csv(roi_id, probs, classes, csv_path)
+
+
+def _write_csv(roi_id, probs, classes, csv_path):
+    csv_path = Path(csv_path)
+    csv_path.parent.mkdir(parents=True, exist_ok=True)
+    # results sorted by ROI id (probability.py:197); .adc order is already ascending
+    if len(roi_id) > 1 and np.any(np.diff(roi_id) < 0):
+        order = np.argsort(roi_id, kind="stable")
+        roi_id, probs = roi_id[order], probs[order]
+    with open(csv_path, "wb") as fh:
+        fh.write(_engine.format_prob_csv(classes, roi_id, probs))

@@ -1,0 +1,552 @@
+// K2: implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM, operands staged by TMA), with the folded-BatchNorm bias, the residual add and the ReLU in
+// the epilogue.  bf16 NHWC activations, fp32 accumulation.
+//
+// Replaces the conv / BatchNorm / ReLU / add sequence of torchvision's ResNet blocks as run by
+// TorchVisionNet.forward (sykepic/train/network.py:66-68) -- in the reference these are cuDNN /
+// oneDNN library calls, there is no kernel source to follow.
+//
+// GEMM view:  D[M = pixels, N = Cout] = sum over taps (r,s) and 64-channel chunks of
+//             A_tap[M, 64] * W_tap[N, 64]^T.
+//   * An M tile is a BOX of 128 output pixels: wb x hb pixels of nb images (wb*hb*nb = 128, chosen
+//     per layer so that no MMA row is wasted).  For filter tap (r,s) the A operand of the tile is
+//     the same box of the INPUT tensor shifted by (r-pad, s-pad): one 4-D TMA tiled load
+//     {64 channels, wb, hb, nb}; out-of-image coordinates are zero-filled by TMA, which is exactly
+//     the convolution's zero padding.  No im2col buffer exists anywhere.
+//   * stride 2: the input is addressed through one tensor map per (row, column) parity, whose W/H
+//     strides are doubled; tap (r,s) selects the map and a shifted box in it.
+//   * The box lands in shared memory as 128 rows of 128 bytes with the 128-byte swizzle, i.e. the
+//     canonical K-major SWIZZLE_128B operand layout of tcgen05.mma; weights [Cout][taps*Cin] are
+//     loaded the same way (2-D map).
+//   * Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+//     (one thread) + TMEM allocation, warps 2-5 = epilogue (tcgen05.ld -> bias/residual/ReLU ->
+//     bf16 stores).  The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps
+//     the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
+#include "spk_internal.h"
+
+namespace spk {
+namespace {
+
+constexpr int kBM = 128;          // pixels per tile (UMMA M)
+constexpr int kBK = 64;           // channels per k block (128 bytes of bf16 = one swizzle row)
+constexpr int kThreads = 192;     // 6 warps
+constexpr int kMaxTaps = 9;
+constexpr int kABytes = kBM * kBK * 2;
+
+struct alignas(64) TcParams {
+  CUtensorMap map_a[4];
+  CUtensorMap map_b;
+  const float* bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+  int n, ho, wo, cout, ldy, ldres, relu;
+  int wb, hb, nb;
+  int tiles_w, tiles_h, tiles_img, tiles_n;
+  int taps, kchunks, cin_pad;
+  int total_tiles;
+  signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    // a pipeline bug must not hang the GPU: give up after ~2 s and raise a launch failure instead
+    if (spin == 64) t0 = clock64();
+    if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 in, fp32 accumulate, M = 128, N from the instruction descriptor
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4 in bits [0,14), leading byte offset (unused for swizzled K-major, 1) in [16,30), stride byte
+// offset = 1024 B between 8-row groups in [32,46), descriptor version 1 in [46,48), layout type
+// SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (power of two)
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10),
+  // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
+  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* gen_base = smem_raw + (base - raw);
+  const uint32_t bar_base = base + C::kStages * C::kStageBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]; then the TMEM base address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&p.map_b);
+    tma_prefetch_desc(&p.map_a[0]);
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
+                 "r"((uint32_t)C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kblocks = p.taps * p.kchunks;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        int m = tile / p.tiles_n;
+        const int twi = m % p.tiles_w;
+        m /= p.tiles_w;
+        const int thi = m % p.tiles_h;
+        const int ng = m / p.tiles_h;
+        const int w0 = twi * p.wb, h0 = thi * p.hb, n0 = ng * p.nb;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / p.kchunks;
+          const int c0 = (kb - tap * p.kchunks) * kBK;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * C::kStageBytes;
+          mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
+          tma_load_4d(sa, &p.map_a[p.tap_map[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          tma_load_2d(sa + kABytes, &p.map_b, full_bar(stage), tap * p.cin_pad + c0, nt * BN);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * C::kStageBytes;
+          const uint64_t a_desc = smem_desc_sw128(sa);
+          const uint64_t b_desc = smem_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            tc_mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // pixel of the tile == TMEM lane
+    const int wbi = row % p.wb;
+    const int hbi = (row / p.wb) % p.hb;
+    const int nbi = row / (p.wb * p.hb);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.tiles_n;
+      int m = tile / p.tiles_n;
+      const int twi = m % p.tiles_w;
+      m /= p.tiles_w;
+      const int thi = m % p.tiles_h;
+      const int ng = m / p.tiles_h;
+      const int wo = twi * p.wb + wbi, ho = thi * p.hb + hbi, img = ng * p.nb + nbi;
+      const bool valid = (wo < p.wo) && (ho < p.ho) && (img < p.n);
+      const long long pix = ((long long)img * p.ho + ho) * p.wo + wo;
+      __nv_bfloat16* yrow = p.y + pix * p.ldy + nt * BN;
+      const __nv_bfloat16* rrow = p.res ? p.res + pix * p.ldres + nt * BN : nullptr;
+      const float* brow = p.bias + nt * BN;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c + j));
+            f[j] = __uint_as_float(v[j]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (rrow) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c + j));
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 rf = __bfloat1622float2(r2[t]);
+                f[j + 2 * t] += rf.x;
+                f[j + 2 * t + 1] += rf.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            o.x = *reinterpret_cast<uint32_t*>(&t0);
+            o.y = *reinterpret_cast<uint32_t*>(&t1);
+            o.z = *reinterpret_cast<uint32_t*>(&t2);
+            o.w = *reinterpret_cast<uint32_t*>(&t3);
+            *reinterpret_cast<uint4*>(yrow + c + j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+
+int pick_bn(int cout) {
+  for (int bn : {256, 128, 64, 32})
+    if (cout % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace
+
+struct TcConvPlan {
+  ConvGeom g;
+  int bn = 0;
+  TcParams prm;
+  __nv_bfloat16* d_w = nullptr;
+  int64_t bytes = 0;
+  const void* x_ptr = nullptr;
+  int n_maps = 0;
+  int map_hp[4], map_wp[4];
+};
+
+bool tc_conv_supported(const ConvGeom& g) {
+  if (g.kh * g.kw > kMaxTaps) return false;
+  if (g.stride != 1 && g.stride != 2) return false;
+  if (g.cin % 8 != 0 || g.cin < 16 || g.ldx % 8 != 0) return false;
+  if (pick_bn(g.cout) == 0) return false;
+  if (g.ldy % 8 != 0 || (g.ldres % 8) != 0) return false;
+  return encode_fn() != nullptr;
+}
+
+static int encode_a_maps(spk_ctx* ctx, TcConvPlan* p, const void* x) {
+  const ConvGeom& g = p->g;
+  EncodeTiledFn enc = encode_fn();
+  for (int i = 0; i < p->n_maps; ++i) {
+    const int hp = p->map_hp[i], wp = p->map_wp[i], s = g.stride;
+    const char* base = (const char*)x + ((size_t)hp * g.w + wp) * g.ldx * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)g.cin, (cuuint64_t)((g.w - wp + s - 1) / s), (cuuint64_t)((g.h - hp + s - 1) / s),
+                          (cuuint64_t)g.n};
+    cuuint64_t strides[3] = {(cuuint64_t)s * g.ldx * 2, (cuuint64_t)s * g.w * g.ldx * 2, (cuuint64_t)g.h * g.w * g.ldx * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)p->prm.wb, (cuuint32_t)p->prm.hb, (cuuint32_t)p->prm.nb};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p->prm.map_a[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(ctx, SPK_ERR_CUDA, "cuTensorMapEncodeTiled(A, %dx%d s%d cin %d, box %dx%dx%d) failed: %d", g.kh, g.kw, s,
+                  g.cin, p->prm.wb, p->prm.hb, p->prm.nb, (int)r);
+  }
+  for (int i = p->n_maps; i < 4; ++i) p->prm.map_a[i] = p->prm.map_a[0];
+  p->x_ptr = x;
+  return SPK_OK;
+}
+
+int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, const float* d_bias, TcConvPlan** out) {
+  if (!tc_conv_supported(g_max)) return fail(ctx, SPK_ERR_UNSUPPORTED, "tcgen05 convolution: unsupported geometry");
+  TcConvPlan* p = new TcConvPlan;
+  p->g = g_max;
+  const ConvGeom& g = p->g;
+  memset(&p->prm, 0, sizeof p->prm);
+  TcParams& prm = p->prm;
+  p->bn = pick_bn(g.cout);
+  prm.bias = d_bias;
+  prm.ho = g.ho;
+  prm.wo = g.wo;
+  prm.cout = g.cout;
+  prm.ldy = g.ldy;
+  prm.ldres = g.ldres;
+  prm.relu = g.relu;
+  prm.taps = g.kh * g.kw;
+  prm.kchunks = (g.cin + kBK - 1) / kBK;
+  prm.cin_pad = prm.kchunks * kBK;
+  prm.tiles_n = g.cout / p->bn;
+
+  // ---- tile box: wb * hb * nb = 128, least padded MMA rows; ties -> larger spatial footprint, wider rows
+  double best = -1;
+  for (int wb = 1; wb <= 128; wb *= 2)
+    for (int hb = 1; wb * hb <= 128; hb *= 2) {
+      const int nb = 128 / (wb * hb);
+      const long long cover = (long long)((g.wo + wb - 1) / wb) * wb * ((g.ho + hb - 1) / hb) * hb * ((g.n + nb - 1) / nb) * nb;
+      const double eff = (double)g.wo * g.ho * g.n / (double)cover;
+      const double score = eff + 1e-4 * (wb * hb) + 1e-6 * wb;
+      if (score > best) {
+        best = score;
+        prm.wb = wb;
+        prm.hb = hb;
+        prm.nb = nb;
+      }
+    }
+  prm.tiles_w = (g.wo + prm.wb - 1) / prm.wb;
+  prm.tiles_h = (g.ho + prm.hb - 1) / prm.hb;
+
+  // ---- taps -> (tensor map, box shift)
+  p->n_maps = 0;
+  for (int r = 0; r < g.kh; ++r)
+    for (int s = 0; s < g.kw; ++s) {
+      const int t = r * g.kw + s;
+      const int th = r - g.pad, tw = s - g.pad;
+      int hp = 0, wp = 0, dh = th, dw = tw;
+      if (g.stride == 2) {
+        hp = ((th % 2) + 2) % 2;
+        wp = ((tw % 2) + 2) % 2;
+        dh = (th - hp) / 2;
+        dw = (tw - wp) / 2;
+      }
+      int mi = -1;
+      for (int i = 0; i < p->n_maps; ++i)
+        if (p->map_hp[i] == hp && p->map_wp[i] == wp) mi = i;
+      if (mi < 0) {
+        mi = p->n_maps++;
+        p->map_hp[mi] = hp;
+        p->map_wp[mi] = wp;
+      }
+      prm.tap_map[t] = (signed char)mi;
+      prm.tap_dh[t] = (signed char)dh;
+      prm.tap_dw[t] = (signed char)dw;
+    }
+
+  // ---- weights: bf16 [Cout][taps][cin_pad], zero padded
+  const size_t kk = (size_t)prm.taps * prm.cin_pad;
+  std::vector<__nv_bfloat16> wb16((size_t)g.cout * kk, __float2bfloat16(0.f));
+  for (int o = 0; o < g.cout; ++o)
+    for (int t = 0; t < prm.taps; ++t)
+      for (int c = 0; c < g.cin; ++c)
+        wb16[(size_t)o * kk + (size_t)t * prm.cin_pad + c] = __float2bfloat16(w[((size_t)o * prm.taps + t) * g.cin + c]);
+  cudaError_t e = cudaMalloc(&p->d_w, wb16.size() * 2);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_w, wb16.data(), wb16.size() * 2, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    tc_conv_plan_destroy(p);
+    return fail(ctx, SPK_ERR_CUDA, "tcgen05 convolution: weight upload: %s", cudaGetErrorString(e));
+  }
+  p->bytes = (int64_t)wb16.size() * 2;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)kk, (cuuint64_t)g.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)kk * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)p->bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(&prm.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_w, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      tc_conv_plan_destroy(p);
+      return fail(ctx, SPK_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+    }
+  }
+  *out = p;
+  return SPK_OK;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* p) {
+  if (!p) return;
+  if (p->d_w) cudaFree(p->d_w);
+  delete p;
+}
+
+int64_t tc_conv_plan_bytes(const TcConvPlan* p) { return p ? p->bytes : 0; }
+
+template <int BN>
+static int launch_bn(spk_ctx* ctx, const TcParams& prm) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    configured = true;
+  }
+  const int grid = std::min(prm.total_tiles, ctx->sm_count);
+  conv_tc_kernel<BN><<<grid, kThreads, C::kSmem, ctx->stream>>>(prm);
+  SPK_LAUNCH_CHECK(ctx);
+  return SPK_OK;
+}
+
+int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y) {
+  if (n <= 0) return SPK_OK;
+  if (n > p->g.n) return fail(ctx, SPK_ERR_CAPACITY, "tcgen05 convolution: batch %d > planned %d", n, p->g.n);
+  if (x != p->x_ptr) {
+    int rc = encode_a_maps(ctx, p, x);
+    if (rc) return rc;
+  }
+  TcParams& prm = p->prm;
+  prm.n = n;
+  prm.res = (const __nv_bfloat16*)res;
+  prm.y = (__nv_bfloat16*)y;
+  prm.tiles_img = (n + prm.nb - 1) / prm.nb;
+  prm.total_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img * prm.tiles_n;
+  switch (p->bn) {
+    case 256: return launch_bn<256>(ctx, prm);
+    case 128: return launch_bn<128>(ctx, prm);
+    case 64: return launch_bn<64>(ctx, prm);
+    case 32: return launch_bn<32>(ctx, prm);
+  }
+  return fail(ctx, SPK_ERR_STATE, "tcgen05 convolution: bad plan");
+}
+
+}  // namespace spk

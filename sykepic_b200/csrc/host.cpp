@@ -1,0 +1,223 @@
+// Host-side entry points of the C ABI: context-free utilities (.adc parsing, geometry
+// validation, .prob.csv formatting, threshold quantisation).  No CUDA here.
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "spk_internal.h"
+
+namespace spk {
+
+std::string& tls_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+int fail(spk_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->error = buf;
+  else
+    tls_error() = buf;
+  return code;
+}
+
+namespace {
+
+inline bool py_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r') || (c >= 0x1c && c <= 0x1f); }
+
+// Python int(str) for the ASCII subset: [ws] [+-] digit (_? digit)* [ws].  false on anything else.
+bool py_int(const char* b, const char* e, int64_t* out) {
+  while (b < e && py_space(*b)) ++b;
+  while (e > b && py_space(e[-1])) --e;
+  if (b >= e) return false;
+  bool neg = false;
+  if (*b == '+' || *b == '-') {
+    neg = (*b == '-');
+    ++b;
+  }
+  if (b >= e || *b < '0' || *b > '9') return false;
+  unsigned long long v = 0;
+  bool prev_us = false;
+  for (; b < e; ++b) {
+    if (*b == '_') {
+      if (prev_us) return false;
+      prev_us = true;
+      continue;
+    }
+    if (*b < '0' || *b > '9') return false;
+    prev_us = false;
+    if (v > (ULLONG_MAX - 9) / 10) return false;
+    v = v * 10 + (unsigned)(*b - '0');
+  }
+  if (prev_us) return false;
+  if (v > (unsigned long long)LLONG_MAX) return false;
+  *out = neg ? -(int64_t)v : (int64_t)v;
+  return true;
+}
+
+}  // namespace
+}  // namespace spk
+
+using namespace spk;
+
+extern "C" {
+
+int spk_abi_version(void) { return SPK_ABI_VERSION; }
+
+const char* spk_last_error(const spk_ctx* ctx) { return ctx ? ctx->error.c_str() : tls_error().c_str(); }
+
+void spk_new_dims(int h, int w, int target_h, int target_w, int* new_h, int* new_w) {
+  new_dims(h, w, target_h, target_w, new_h, new_w);
+}
+
+int spk_adc_parse(const char* text, int64_t len, int64_t cap, int32_t* roi_id, int32_t* width, int32_t* height,
+                  int64_t* start, int64_t* n_out, int64_t* n_lines) {
+  if (!text || len < 0 || !n_out) return fail(nullptr, SPK_ERR_INVALID, "spk_adc_parse: bad arguments");
+  int64_t n = 0, line_no = 0;
+  const char* p = text;
+  const char* end = text + len;
+  while (p < end) {
+    const char* eol = p;
+    while (eol < end && *eol != '\n' && *eol != '\r') ++eol;
+    ++line_no;
+    // fields 15, 16, 17 of the comma-split line
+    const char* fb[3] = {nullptr, nullptr, nullptr};
+    const char* fe[3] = {nullptr, nullptr, nullptr};
+    int field = 0;
+    const char* q = p;
+    const char* fstart = p;
+    for (;; ++q) {
+      if (q == eol || *q == ',') {
+        if (field >= 15 && field <= 17) {
+          fb[field - 15] = fstart;
+          fe[field - 15] = q;
+        }
+        ++field;
+        fstart = q + 1;
+        if (q == eol || field > 17) break;
+      }
+    }
+    if (field < 18)
+      return fail(nullptr, SPK_ERR_PARSE, ".adc line %lld has %d fields, need at least 18", (long long)line_no, field);
+    int64_t v[3];
+    for (int i = 0; i < 3; ++i)
+      if (!py_int(fb[i], fe[i], &v[i]))
+        return fail(nullptr, SPK_ERR_PARSE, ".adc line %lld: field %d is not an integer", (long long)line_no, 15 + i);
+    if (v[0] >= 1 && v[1] >= 1) {
+      if (v[0] > INT32_MAX || v[1] > INT32_MAX)
+        return fail(nullptr, SPK_ERR_PARSE, ".adc line %lld: ROI size out of range", (long long)line_no);
+      if (n >= cap) return fail(nullptr, SPK_ERR_CAPACITY, "spk_adc_parse: more than %lld ROIs", (long long)cap);
+      if (roi_id) roi_id[n] = (int32_t)line_no;
+      if (width) width[n] = (int32_t)v[0];
+      if (height) height[n] = (int32_t)v[1];
+      if (start) start[n] = v[2];
+      ++n;
+    }
+    // universal newlines: \r\n counts once
+    p = eol;
+    if (p < end) {
+      if (*p == '\r' && p + 1 < end && p[1] == '\n')
+        p += 2;
+      else
+        p += 1;
+    }
+  }
+  *n_out = n;
+  if (n_lines) *n_lines = line_no;
+  return SPK_OK;
+}
+
+int spk_rois_validate(const int32_t* width, const int32_t* height, const int64_t* start, int64_t n, int64_t roi_len,
+                      int target_h, int target_w, int64_t* first_bad) {
+  if (first_bad) *first_bad = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t w = width[i], h = height[i], s = start[i];
+    // numpy slicing: a negative start counts from the end; the slice is never longer than asked
+    int64_t lo = s < 0 ? (s + roi_len < 0 ? 0 : s + roi_len) : (s > roi_len ? roi_len : s);
+    int64_t stop = s + w * h;
+    int64_t hi = stop < 0 ? (stop + roi_len < 0 ? 0 : stop + roi_len) : (stop > roi_len ? roi_len : stop);
+    int64_t got = hi > lo ? hi - lo : 0;
+    if (w < 1 || h < 1 || got != w * h || s < 0) {
+      if (first_bad) *first_bad = i;
+      return fail(nullptr, SPK_ERR_FAULTY_BIN, "ROI %lld (%lldx%lld @%lld) runs past the %lld .roi bytes",
+                  (long long)i, (long long)w, (long long)h, (long long)s, (long long)roi_len);
+    }
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    int nh, nw;
+    new_dims(height[i], width[i], target_h, target_w, &nh, &nw);
+    if (nh < 1 || nw < 1) {
+      if (first_bad) *first_bad = i;
+      return fail(nullptr, SPK_ERR_EMPTY_RESIZE, "ROI %lld (%dx%d) resizes to %dx%d", (long long)i, width[i], height[i],
+                  nw, nh);
+    }
+  }
+  return SPK_OK;
+}
+
+int32_t spk_threshold_quantize(double thr, int strict) {
+  // value(q) = the double nearest to q/1e5 (what float("%.5f") parses to); monotone in q.
+  if (std::isnan(thr)) return INT32_MAX;
+  auto value = [](int64_t q) { return (double)q / 100000.0; };  // correctly rounded division == strtod of the decimal
+  double guess = std::ceil(thr * 100000.0);
+  if (guess > 2.0e9) return INT32_MAX;
+  if (guess < -2.0e9) return INT32_MIN;
+  int64_t q = (int64_t)guess;
+  auto ok = [&](int64_t k) { return strict ? value(k) > thr : value(k) >= thr; };
+  while (ok(q - 1)) --q;
+  while (!ok(q)) ++q;
+  if (q > INT32_MAX) return INT32_MAX;
+  if (q < INT32_MIN) return INT32_MIN;
+  return (int32_t)q;
+}
+
+int spk_format_prob_csv(const char* header_line, const int32_t* roi_id, const float* probs, int64_t n, int k, char* out,
+                        int64_t cap, int64_t* len) {
+  if (!header_line || !len || n < 0 || k < 0) return fail(nullptr, SPK_ERR_INVALID, "spk_format_prob_csv: bad arguments");
+  int64_t pos = 0;
+  auto put = [&](const char* s, int64_t m) {
+    if (out && pos + m <= cap) memcpy(out + pos, s, (size_t)m);
+    pos += m;
+  };
+  put(header_line, (int64_t)strlen(header_line));
+  char tmp[64];
+  for (int64_t i = 0; i < n; ++i) {
+    int m = snprintf(tmp, sizeof tmp, "%d", roi_id[i]);
+    put(tmp, m);
+    const float* row = probs + i * (int64_t)k;
+    for (int j = 0; j < k; ++j) {
+      float p = row[j];
+      if (p >= 0.0f && p <= 1.0f) {
+        // p * 1e5 is exact in double (24-bit x 17-bit); rint = round-half-even of the exact value,
+        // which is what a correctly rounded "%.5f" prints.
+        unsigned q = (unsigned)std::nearbyint((double)p * 100000.0);
+        char* t = tmp;
+        *t++ = ',';
+        *t++ = (char)('0' + q / 100000u);
+        unsigned f = q % 100000u;
+        *t++ = '.';
+        t[4] = (char)('0' + f % 10u); f /= 10u;
+        t[3] = (char)('0' + f % 10u); f /= 10u;
+        t[2] = (char)('0' + f % 10u); f /= 10u;
+        t[1] = (char)('0' + f % 10u); f /= 10u;
+        t[0] = (char)('0' + f % 10u);
+        put(tmp, 8);
+      } else {
+        m = snprintf(tmp, sizeof tmp, ",%.5f", (double)p);  // nan / out of range: defer to libc
+        put(tmp, m);
+      }
+    }
+    put("\n", 1);
+  }
+  *len = pos;
+  if (out && pos > cap) return fail(nullptr, SPK_ERR_CAPACITY, "spk_format_prob_csv: need %lld bytes", (long long)pos);
+  return SPK_OK;
+}
+
+}  // extern "C"

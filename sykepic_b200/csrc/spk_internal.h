@@ -1,0 +1,108 @@
+// Internal declarations shared by the translation units of libsykepic_b200.so.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "sykepic_b200.h"
+
+namespace spk {
+
+constexpr int kMaxTarget = 512;  // largest supported target side (T_h, T_w)
+
+struct Net;  // net.cu
+
+}  // namespace spk
+
+struct spk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string error;
+  int64_t launches = 0;
+  unsigned long long* d_faults = nullptr;  // device-side count of ROIs with invalid geometry
+  float* d_default_lut = nullptr;          // 3*256: v/255 (true fp32 division)
+  spk::Net* net = nullptr;
+  int sm_count = 148;
+};
+
+namespace spk {
+
+// thread-local message for failures that have no context
+std::string& tls_error();
+
+int fail(spk_ctx* ctx, int code, const char* fmt, ...);
+
+#define SPK_CUDA_OK(ctx, expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return spk::fail((ctx), SPK_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr,      \
+                       cudaGetErrorString(_e));                                             \
+  } while (0)
+
+#define SPK_LAUNCH_CHECK(ctx)                                                               \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return spk::fail((ctx), SPK_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,  \
+                       cudaGetErrorString(_e));                                             \
+  } while (0)
+
+// get_new_dims of sykepic/train/image.py:183-198, shared by host and device code
+__host__ __device__ inline void new_dims(int h, int w, int th, int tw, int* nh, int* nw) {
+  if (h > w) {
+    double r = (double)th / (double)h;
+    *nh = th;
+    *nw = (int)((double)w * r);
+  } else {
+    double r = (double)tw / (double)w;
+    *nh = (int)((double)h * r);
+    *nw = tw;
+  }
+}
+
+// ---- kernels' host launchers (each enqueues on ctx->stream) ---------------------------------
+// preprocess.cu
+int init_default_lut(spk_ctx* ctx);
+// conv_simt.cu
+struct ConvGeom {
+  int n, h, w, cin;         // input NHWC
+  int ho, wo, cout;         // output NHWC
+  int kh, kw, stride, pad;
+  int relu;
+  // channel strides of the pixel rows (>= cin / cout when the tensor is a channel slice of a wider
+  // concat buffer, DenseNet); x / y / res pointers already include the channel offset.
+  int ldx, ldy, ldres;
+};
+int launch_conv_simt(spk_ctx* ctx, const ConvGeom& g, const void* x, int x_dtype, const float* w_kc /*[K][Cout]*/,
+                     const float* bias, const void* res, void* y, int y_dtype);
+int launch_maxpool(spk_ctx* ctx, int n, int h, int w, int c, int k, int stride, int pad, int ho, int wo, int ldy,
+                   const void* x, void* y, int dtype);
+int launch_avgpool(spk_ctx* ctx, int n, int h, int w, int c, int ldx, int k, int stride, int ho, int wo, int ldy,
+                   const void* x, void* y, int dtype);
+int launch_affine_relu(spk_ctx* ctx, long long pixels, int c, int ldx, const float* scale, const float* shift,
+                       const void* x, void* y, int dtype, int relu);
+// head.cu
+int launch_head(spk_ctx* ctx, const void* act, int act_dtype, int64_t n, int hw, int feat, const float* w_kf /*[K][F]*/,
+                const float* bias, int k, float softmax_scale, const int32_t* thr_q, float* logits, float* probs,
+                int32_t* label, uint8_t* classified);
+// conv_tc.cu (tcgen05 / TMEM / TMA implicit GEMM)
+struct TcConvPlan;
+bool tc_conv_supported(const ConvGeom& g);
+int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
+                        const float* bias, TcConvPlan** out);
+void tc_conv_plan_destroy(TcConvPlan* p);
+int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y);
+int64_t tc_conv_plan_bytes(const TcConvPlan* p);
+// stem.cu: conv 7x7/2 (1 input plane) + bias + ReLU + maxpool 3x3/2, u8 in -> bf16 NHWC out
+int launch_stem_u8(spk_ctx* ctx, int n, int t_h, int t_w, const uint8_t* x, const float* lut256, const float* w_k64 /*[49][64]*/,
+                   const float* bias, __nv_bfloat16* y, int hp, int wp);
+
+}  // namespace spk

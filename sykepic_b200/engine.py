@@ -1,0 +1,405 @@
+"""Per-GPU inference engine: the Python host of the C-ABI library.
+
+One `Engine` owns one `spk_ctx` (one GPU, one CUDA stream).  PyTorch is used only
+to read the checkpoint (`torch.load` of the reference's `best_state.pth`
+state_dict) and to own pinned-host / device buffers; every computation is a
+call into libsykepic_b200.so.
+
+Reference behaviour mirrored here:
+  * model directory layout and `config.ini` keys: `prepare_model`
+    sykepic/compute/probability.py:118-130, `get_img_shape` / `get_transforms` /
+    `get_network` sykepic/train/config.py:20-77;
+  * network structure: `TorchVisionNet` sykepic/train/network.py:11-72 over
+    torchvision ResNet / DenseNet, described to the library from the state_dict keys;
+  * per-bin flow: `process_sample` + `net_pass` probability.py:133-197.
+"""
+
+import ctypes as C
+import re
+from configparser import ConfigParser, NoOptionError
+from pathlib import Path
+
+import numpy as np
+
+from . import _lib
+from ._lib import ptr
+
+SOFTMAX_EXP = 1.3  # sykepic/compute/probability.py:18
+BN_EPS = 1e-5  # torch.nn.BatchNorm2d default (torchvision resnet / densenet)
+
+
+class ModelSpec:
+    """What the reference's `prepare_model` reads from a model directory."""
+
+    def __init__(self, classes, img_shape, border, arch, state_dict, imagenet_normalization=False):
+        self.classes = list(classes)
+        self.img_shape = tuple(img_shape)
+        self.border = border
+        self.arch = arch
+        self.state_dict = state_dict
+        # sykepic/train/config.py:55-56 appends Normalize to the TRAIN transform only; the eval
+        # transform of the prob path never normalises.  Kept for information.
+        self.imagenet_normalization = imagenet_normalization
+
+    @classmethod
+    def from_dir(cls, model_dir):
+        import torch
+
+        model_dir = Path(model_dir)
+        with open(model_dir / "class_names.txt") as fh:
+            classes = fh.read().splitlines()
+        config = ConfigParser()
+        config.read(model_dir / "config.ini")
+        img_shape = tuple(int(i) for i in config.get("image", "shape").split(","))
+        border = config.get("image", "border")
+        if border not in _lib.BORDER:
+            # image.py:20-28 silently leaves self.border unset for unknown names and fails later
+            raise ValueError(f"unknown border {border!r} in {model_dir / 'config.ini'}")
+        try:
+            norm = config.getboolean("image", "imagenet_normalization")
+        except (NoOptionError, ValueError):
+            norm = False
+        arch = config.get("model", "network")
+        # the `weights` key only selects what torchvision downloads before load_state_dict
+        # overwrites it (config.py:65-70); nothing is ever downloaded here.
+        sd = torch.load(model_dir / "best_state.pth", map_location="cpu", weights_only=True)
+        return cls(classes, img_shape, border, arch, sd, norm)
+
+
+def _np(sd, key):
+    t = sd[key]
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().float().numpy()
+    return np.ascontiguousarray(t, dtype=np.float32)
+
+
+class _IdPool:
+    def __init__(self, first=1):
+        self.next = first
+        self.free = []
+
+    def get(self):
+        if self.free:
+            return self.free.pop()
+        i = self.next
+        self.next += 1
+        return i
+
+    def put(self, i):
+        if i is not None and i not in self.free:
+            self.free.append(i)
+
+
+class Engine:
+    """B200 engine for one model.  `precision`: "fp32" (CUDA-core FFMA convolutions, probabilities
+    within 1e-4 of the reference) or "bf16" (tcgen05 tensor-core convolutions, within 2e-2)."""
+
+    def __init__(self, spec, device=0, precision="bf16", max_batch=256, conv_impl="auto", stream=None):
+        import torch
+
+        if not isinstance(spec, ModelSpec):
+            spec = ModelSpec.from_dir(spec)
+        self.spec = spec
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SpkError(_lib.SPK_ERR_CUDA, "no CUDA device: sykepic_b200 has no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
+        self.precision_name = precision
+        self.conv_impl = {"auto": _lib.CONV_AUTO, "simt": _lib.CONV_SIMT, "tcgen05": _lib.CONV_TCGEN05}[conv_impl]
+        self.max_batch = int(max_batch)
+        c, th, tw = spec.img_shape
+        if c != 3:
+            # data.py:220-223 builds a [1,T,T] tensor that no torchvision backbone accepts unmodified
+            raise ValueError(f"image shape {spec.img_shape}: only 3-channel models are supported")
+        self.th, self.tw = th, tw
+        self.k = len(spec.classes)
+        with torch.cuda.device(self.device):
+            self.stream = stream or torch.cuda.Stream(device=self.device)
+        self.ctx = C.c_void_p()
+        _lib.check(self.lib.spk_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(self.ctx)))
+        self._keep = []  # numpy arrays referenced by the library during graph construction
+        self._build_graph()
+        self.softmax_scale = float(np.float32(np.log(SOFTMAX_EXP)))  # probability.py:192-193
+        self._x = torch.empty((self.max_batch, th, tw), dtype=torch.uint8, device=self.device)
+        self._thr_dev = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "ctx", None) and self.ctx.value:
+            self.lib.spk_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _lib.check(rc, self.ctx)
+
+    @property
+    def launches(self):
+        return int(self.lib.spk_launch_count(self.ctx))
+
+    def net_bytes(self):
+        return int(self.lib.spk_net_bytes(self.ctx))
+
+    # ------------------------------------------------------------------ graph construction
+    def _conv(self, sd, wkey, bnkey, inb, outb, stride, pad, relu, res=-1, in_off=0, out_off=0):
+        w = _np(sd, wkey)
+        cout, cin, kh, kw = w.shape
+        bn = [None] * 4
+        if bnkey is not None:
+            bn = [_np(sd, f"{bnkey}.{n}") for n in ("weight", "bias", "running_mean", "running_var")]
+        self._keep.extend([w, *bn])
+        self._ck(self.lib.spk_net_conv(self.ctx, inb, in_off, outb, out_off, res, ptr(w), cout, cin, kh, kw, stride, pad,
+                                       ptr(bn[0]), ptr(bn[1]), ptr(bn[2]), ptr(bn[3]), BN_EPS, None, int(relu),
+                                       self.conv_impl))
+        return cout
+
+    def _bn_relu(self, sd, bnkey, inb, outb, channels, relu=True):
+        bn = [_np(sd, f"{bnkey}.{n}") for n in ("weight", "bias", "running_mean", "running_var")]
+        self._keep.extend(bn)
+        self._ck(self.lib.spk_net_bn_relu(self.ctx, inb, outb, channels, ptr(bn[0]), ptr(bn[1]), ptr(bn[2]), ptr(bn[3]),
+                                          BN_EPS, int(relu)))
+
+    def _build_graph(self):
+        sd = self.spec.state_dict
+        self._ck(self.lib.spk_net_begin(self.ctx, self.th, self.tw, 1, self.precision, self.max_batch))
+        if "base.0.conv0.weight" in sd:
+            feat_buf = self._build_densenet(sd)
+        elif "base.0.weight" in sd and "base.4.0.conv1.weight" in sd:
+            feat_buf = self._build_resnet(sd)
+        else:
+            raise ValueError(f"unsupported network {self.spec.arch!r}: state_dict is neither a torchvision ResNet nor DenseNet")
+        # head: every head.<i>.weight in index order (Dropout entries have no parameters; network.py:56-63)
+        idx = sorted(int(m.group(1)) for k in sd if (m := re.fullmatch(r"head\.(\d+)\.weight", k)))
+        ws = [_np(sd, f"head.{i}.weight") for i in idx]
+        bs = [_np(sd, f"head.{i}.bias") for i in idx]
+        dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+        if dims[-1] != self.k:
+            raise ValueError(f"checkpoint has {dims[-1]} outputs, class_names.txt has {self.k} classes")
+        n = len(ws)
+        wp = (C.c_void_p * n)(*[ptr(w) for w in ws])
+        bp = (C.c_void_p * n)(*[ptr(b) for b in bs])
+        dm = (C.c_int * (n + 1))(*dims)
+        self._ck(self.lib.spk_net_head(self.ctx, feat_buf, n, wp, bp, dm))
+        self._ck(self.lib.spk_net_end(self.ctx))
+        self._keep.clear()
+
+    def _build_resnet(self, sd):
+        """torchvision ResNet children()[:-1] (conv1, bn1, relu, maxpool, layer1-4, avgpool) from the
+        `base.<i>` keys TorchVisionNet produces (network.py:48-62)."""
+        ids = _IdPool()
+        a = ids.get()
+        self._conv(sd, "base.0.weight", "base.1", 0, a, 2, 3, True)
+        x = ids.get()
+        self._ck(self.lib.spk_net_maxpool(self.ctx, a, x, 3, 2, 1))
+        ids.put(a)
+        for stage in (4, 5, 6, 7):
+            blocks = sorted({int(m.group(1)) for k in sd if (m := re.match(rf"base\.{stage}\.(\d+)\.", k))})
+            for b in blocks:
+                p = f"base.{stage}.{b}"
+                stride = 2 if (stage > 4 and b == 0) else 1
+                bottleneck = f"{p}.conv3.weight" in sd
+                identity, ds = x, None
+                if f"{p}.downsample.0.weight" in sd:
+                    ds = ids.get()
+                    self._conv(sd, f"{p}.downsample.0.weight", f"{p}.downsample.1", x, ds, stride, 0, False)
+                    identity = ds
+                t1 = ids.get()
+                if bottleneck:  # 1x1 -> 3x3 (stride here: torchvision "v1.5") -> 1x1
+                    self._conv(sd, f"{p}.conv1.weight", f"{p}.bn1", x, t1, 1, 0, True)
+                    t2 = ids.get()
+                    self._conv(sd, f"{p}.conv2.weight", f"{p}.bn2", t1, t2, stride, 1, True)
+                    out = ids.get()
+                    self._conv(sd, f"{p}.conv3.weight", f"{p}.bn3", t2, out, 1, 0, True, res=identity)
+                    ids.put(t2)
+                else:
+                    self._conv(sd, f"{p}.conv1.weight", f"{p}.bn1", x, t1, stride, 1, True)
+                    out = ids.get()
+                    self._conv(sd, f"{p}.conv2.weight", f"{p}.bn2", t1, out, 1, 1, True, res=identity)
+                ids.put(t1)
+                ids.put(ds)
+                ids.put(x)
+                x = out
+        return x
+
+    def _build_densenet(self, sd):
+        """torchvision DenseNet forward: features -> ReLU -> global average pool, then the syke-pic
+        head.  The reference's TorchVisionNet raises for DenseNet at these sizes;
+        this is the defined behaviour ("reference-undefined; parity vs torchvision")."""
+        p = "base.0."
+        ids = _IdPool()
+        h = (self.th + 6 - 7) // 2 + 1
+        w = (self.tw + 6 - 7) // 2 + 1
+        a = ids.get()
+        c = self._conv(sd, p + "conv0.weight", p + "norm0", 0, a, 2, 3, True)
+        h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        blk = 1
+        src, src_kind = a, "maxpool"
+        t1, t2 = ids.get(), ids.get()
+        while (p + f"denseblock{blk}.denselayer1.norm1.weight") in sd:
+            nl = 1
+            while (p + f"denseblock{blk}.denselayer{nl + 1}.norm1.weight") in sd:
+                nl += 1
+            growth = sd[p + f"denseblock{blk}.denselayer1.conv2.weight"].shape[0]
+            total = c + nl * growth
+            cat = ids.get()
+            self._ck(self.lib.spk_net_buffer(self.ctx, cat, h, w, total))
+            if src_kind == "maxpool":
+                self._ck(self.lib.spk_net_maxpool(self.ctx, src, cat, 3, 2, 1))
+            else:
+                self._ck(self.lib.spk_net_avgpool(self.ctx, src, cat, 2, 2))
+            for layer in range(1, nl + 1):
+                q = p + f"denseblock{blk}.denselayer{layer}"
+                self._bn_relu(sd, q + ".norm1", cat, t1, c)
+                self._conv(sd, q + ".conv1.weight", q + ".norm2", t1, t2, 1, 0, True)
+                self._conv(sd, q + ".conv2.weight", None, t2, cat, 1, 1, False, out_off=c)
+                c += growth
+            t = p + f"transition{blk}"
+            if (t + ".norm.weight") not in sd:
+                self._bn_relu(sd, p + "norm5", cat, t1, c)
+                return t1
+            # transition: BN -> ReLU -> 1x1 conv -> 2x2 average pool (into the next block's buffer)
+            self._bn_relu(sd, t + ".norm", cat, t1, c)
+            src, src_kind = ids.get(), "avgpool"
+            c = self._conv(sd, t + ".conv.weight", None, t1, src, 1, 0, False)
+            h, w = h // 2, w // 2
+            blk += 1
+        raise ValueError("DenseNet state_dict without a final dense block")
+
+    # ------------------------------------------------------------------ thresholds
+    def set_thresholds(self, thresholds):
+        """Per-class thresholds for the fused label rule (sykepic/compute/prediction.py:49-71).
+
+        `thresholds`: dict name -> float (classes without an entry can never be "classified"),
+        a number (scalar rule: idxmax, classified iff p > thr) or None."""
+        torch = self.torch
+        self._thr_scalar_q = None
+        if thresholds is None:
+            self._thr_dev = None
+            return
+        if isinstance(thresholds, (int, float)):
+            self._thr_scalar_q = int(self.lib.spk_threshold_quantize(float(thresholds), 1))
+            self._thr_dev = None
+            return
+        q = np.full(self.k, _lib.INT32_MAX, np.int32)
+        for i, name in enumerate(self.spec.classes):
+            if name in thresholds:
+                q[i] = self.lib.spk_threshold_quantize(float(thresholds[name]), 0)
+        self._thr_dev = torch.from_numpy(q).to(self.device)
+
+    # ------------------------------------------------------------------ device steps
+    def preprocess(self, roi_dev, roi_len, start_dev, w_dev, h_dev, n, out, out_dtype=_lib.DTYPE_U8, channels=1,
+                   layout=_lib.LAYOUT_NCHW, offset=0):
+        """K1 on `n` ROIs starting at descriptor `offset` (device tensors)."""
+        self._ck(self.lib.spk_preprocess(
+            self.ctx, ptr(roi_dev), roi_len, start_dev.data_ptr() + 8 * offset, w_dev.data_ptr() + 4 * offset,
+            h_dev.data_ptr() + 4 * offset, n, self.th, self.tw, _lib.BORDER[self.spec.border], channels, out_dtype,
+            layout, None, ptr(out)))
+
+    def forward(self, x_u8, n, probs_out, label_out=None, classified_out=None):
+        """K2 + K3 on a preprocessed u8 batch [n, T, T]."""
+        self._ck(self.lib.spk_forward(self.ctx, ptr(x_u8), n, self.softmax_scale, ptr(self._thr_dev), ptr(probs_out),
+                                      ptr(label_out), ptr(classified_out)))
+
+    def fault_count(self):
+        v = C.c_int64()
+        self._ck(self.lib.spk_fault_count(self.ctx, C.byref(v)))
+        return v.value
+
+    def synchronize(self):
+        self._ck(self.lib.spk_synchronize(self.ctx))
+
+    # ------------------------------------------------------------------ one bin
+    def run_bin_device(self, roi_dev, roi_len, start_dev, w_dev, h_dev, n, probs_dev, label_dev=None, cls_dev=None,
+                       batch_size=None):
+        """Decode + transform + network for the `n` ROIs of one bin, everything already on the device."""
+        bs = min(batch_size or self.max_batch, self.max_batch)
+        for i in range(0, n, bs):
+            m = min(bs, n - i)
+            self.preprocess(roi_dev, roi_len, start_dev, w_dev, h_dev, m, self._x, offset=i)
+            self.forward(self._x, m, probs_dev[i:i + m], None if label_dev is None else label_dev[i:i + m],
+                         None if cls_dev is None else cls_dev[i:i + m])
+
+    def run_bin(self, adc_text, roi_bytes, batch_size=None, want_labels=False):
+        """.adc text + .roi bytes (host) -> (roi_id int32[N], probs float32[N,K][, label, classified]).
+
+        Raises `FaultyBin` (ValueError) when a ROI runs past the .roi bytes and `EmptyResize`
+        when a ROI would resize to a 0-pixel side -- the two cases in which the reference skips
+        the whole bin (probability.py:111-114)."""
+        roi_id, w, h, start = parse_adc(adc_text)
+        roi_np = np.frombuffer(roi_bytes, dtype=np.uint8) if not isinstance(roi_bytes, np.ndarray) else roi_bytes
+        out = self.run_rois(roi_id, w, h, start, roi_np, batch_size, want_labels)
+        return (roi_id, *out) if want_labels else (roi_id, out)
+
+    def run_rois(self, roi_id, w, h, start, roi_np, batch_size=None, want_labels=False):
+        """ROI descriptors + the byte stream they index (host numpy) -> probs float32[N,K]
+        (or (probs, label int32[N], classified bool[N]))."""
+        torch = self.torch
+        n = len(w)
+        w = np.ascontiguousarray(w, np.int32)
+        h = np.ascontiguousarray(h, np.int32)
+        start = np.ascontiguousarray(start, np.int64)
+        roi_np = np.ascontiguousarray(roi_np, np.uint8)
+        validate_rois(w, h, start, roi_np.size, self.th, self.tw)
+        if n == 0:
+            probs_h = np.zeros((0, self.k), np.float32)
+            return (probs_h, np.zeros(0, np.int32), np.zeros(0, bool)) if want_labels else probs_h
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            roi_dev = torch.from_numpy(roi_np).to(self.device, non_blocking=True)
+            start_dev = torch.from_numpy(start).to(self.device, non_blocking=True)
+            w_dev = torch.from_numpy(w).to(self.device, non_blocking=True)
+            h_dev = torch.from_numpy(h).to(self.device, non_blocking=True)
+            probs = torch.empty((n, self.k), dtype=torch.float32, device=self.device)
+            label = torch.empty(n, dtype=torch.int32, device=self.device) if want_labels else None
+            cls = torch.empty(n, dtype=torch.uint8, device=self.device) if want_labels else None
+            self.run_bin_device(roi_dev, roi_np.size, start_dev, w_dev, h_dev, n, probs, label, cls, batch_size)
+            probs_h = probs.cpu().numpy()
+            if want_labels:
+                return probs_h, label.cpu().numpy(), cls.cpu().numpy().astype(bool)
+        return probs_h
+
+
+# ---------------------------------------------------------------------- host helpers over the C ABI
+def parse_adc(adc_text):
+    """.adc text (str or bytes) -> (roi_id int32[N], width int32[N], height int32[N], start int64[N]).
+
+    sykepic/utils/ifcb.py:101-110: ROI id = 1-based line number, rows with width or height < 1 skipped."""
+    lib = _lib.load()
+    data = adc_text.encode() if isinstance(adc_text, str) else bytes(adc_text)
+    cap = data.count(b"\n") + data.count(b"\r") + 1
+    roi_id = np.empty(cap, np.int32)
+    w = np.empty(cap, np.int32)
+    h = np.empty(cap, np.int32)
+    start = np.empty(cap, np.int64)
+    n = C.c_int64()
+    lines = C.c_int64()
+    _lib.check(lib.spk_adc_parse(data, len(data), cap, ptr(roi_id), ptr(w), ptr(h), ptr(start), C.byref(n), C.byref(lines)))
+    k = n.value
+    return roi_id[:k].copy(), w[:k].copy(), h[:k].copy(), start[:k].copy()
+
+
+def validate_rois(w, h, start, roi_len, th, tw):
+    lib = _lib.load()
+    bad = C.c_int64()
+    _lib.check(lib.spk_rois_validate(ptr(w), ptr(h), ptr(start), len(w), int(roi_len), th, tw, C.byref(bad)))
+
+
+def format_prob_csv(classes, roi_id, probs):
+    """bytes of the .prob.csv (sykepic/compute/probability.py:200-206)."""
+    lib = _lib.load()
+    header = ("roi," + ",".join(classes) + "\n").encode()
+    roi_id = np.ascontiguousarray(roi_id, dtype=np.int32)
+    probs = np.ascontiguousarray(probs, dtype=np.float32)
+    n = len(roi_id)
+    k = probs.shape[1] if probs.ndim == 2 else len(classes)
+    cap = len(header) + n * (12 + 8 * k + 1) + 16
+    buf = C.create_string_buffer(cap)
+    ln = C.c_int64()
+    _lib.check(lib.spk_format_prob_csv(header, ptr(roi_id), ptr(probs), n, k, buf, cap, C.byref(ln)))
+    return buf.raw[:ln.value]
