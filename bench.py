@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the syke-pic prob hot path on B200 (BASELINE.json metric: IFCB ROIs/s, bin -> class probs).
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU arm (oracle port of the reference)
+
+A step = one pass of the hot path (K1 decode/resize/normalise -> K2 CNN -> K3 pool/head/softmax/
+threshold) over one batch of synthetic IFCB ROIs.  Default workload = BASELINE.json configs[1]:
+ResNet-18, 3x224x224, batch 256 per GPU, BF16, random-init weights (seeded), synthetic ROIs with the
+IFCB size distribution (sykepic_b200/synth.py).  Multi-GPU = bins sharded over ranks, no collective
+on the data path (weak scaling); NCCL is used only for the barrier and the max-over-ranks time.
+
+Prints ONE JSON line (rank 0).  `value`: device-timed throughput with the batch resident in HBM;
+`e2e`: the same through the host API (`Engine.run_rois`: pinned host buffers -> H2D -> kernels -> D2H);
+`roofline`: the tcgen05 convolution kernels against the measured BF16 peak; `cpu_baseline`: the oracle
+port timed on this box's host cores on a bounded sample.
+"""
+
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "ifcb_rois_per_s"
+UNIT = "ROIs/s"
+FLUSH_BYTES = 256 << 20
+
+# conv FLOPs / ROI at 224x224 with un-padded logical shapes -- informational
+CONV_GFLOP = {"resnet18": 3.627, "resnet50": 8.174, "densenet121": 5.666}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--arch", default="resnet18")
+    ap.add_argument("--batch", type=int, default=None, help="ROIs per step per GPU (default 256; 512 for resnet50/densenet121)")
+    ap.add_argument("--target", type=int, default=224)
+    ap.add_argument("--precision", choices=("bf16", "fp32"), default="bf16")
+    ap.add_argument("--conv-impl", choices=("auto", "simt", "tcgen05"), default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-detail", metavar="FILE", help="write the per-launch timing table of the roofline pass")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def workload(args, seed, n_batches):
+    """n_batches batches of `batch` non-empty synthetic ROIs -> list of (w, h, start, roi_bytes)."""
+    from sykepic_b200 import synth
+
+    out = []
+    for i in range(n_batches):
+        b = synth.synth_bin(seed + i, int(args.batch * 1.01) + 8)
+        keep = np.flatnonzero(b["w"] > 0)[: args.batch]
+        assert len(keep) == args.batch
+        out.append((b["w"][keep].astype(np.int32), b["h"][keep].astype(np.int32), b["start"][keep].astype(np.int64), b["roi_bytes"]))
+    return out
+
+
+def model_dir(args, root):
+    from sykepic_b200 import synth
+
+    return synth.write_model_dir(Path(root) / f"model_{args.arch}", arch=args.arch, t=args.target, head=(256, 128), seed=0,
+                                 border="mode", imagenet_normalization=False, randomize_bn=True, logit_gain=8.0)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self._halt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                break
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(args, mdir, batches, budget_s, max_rois=4096, chunk=64):
+    """The oracle (numpy + torch-CPU restatement of the reference path) on this box's host cores."""
+    import torch
+
+    from oracle import network, pipeline
+
+    model = pipeline.prepare_model(mdir)
+    w, h, start, roi = batches[0]
+    done, t_used = 0, 0.0
+    i = 0
+    # one untimed chunk to page everything in
+    with torch.no_grad():
+        while done < max_rois and (t_used < budget_s or done == 0):
+            lo = (i * chunk) % len(w)
+            idx = range(lo, min(lo + chunk, len(w)))
+            t0 = time.perf_counter()
+            imgs = [roi[start[k]:start[k] + int(w[k]) * int(h[k])].reshape(int(h[k]), int(w[k])) for k in idx]
+            x = torch.from_numpy(pipeline.preprocess_rois(model, imgs))
+            probs = network.probabilities(network.forward_logits(model.state_dict, x))
+            probs.tolist()
+            dt = time.perf_counter() - t0
+            if i > 0:  # chunk 0 is warm-up
+                done += len(imgs)
+                t_used += dt
+            i += 1
+    return done / t_used, done, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    import torch
+
+    args.batch = args.batch or (256 if args.arch == "resnet18" else 512)
+    tmp = tempfile.mkdtemp(prefix="spk_bench_")
+    mdir = model_dir(args, tmp)
+    batches = workload(args, 2000, 1)
+    from oracle import network, pipeline
+
+    model = pipeline.prepare_model(mdir)
+    w, h, start, roi = batches[0]
+    # a step of the CPU arm = a bounded sample (64 ROIs) of the batch, all host threads
+    sample = min(64, args.batch)
+
+    def step(i):
+        lo = (i * sample) % (len(w) - sample + 1)
+        imgs = [roi[start[k]:start[k] + int(w[k]) * int(h[k])].reshape(int(h[k]), int(w[k])) for k in range(lo, lo + sample)]
+        x = torch.from_numpy(pipeline.preprocess_rois(model, imgs))
+        with torch.no_grad():
+            network.probabilities(network.forward_logits(model.state_dict, x)).tolist()
+
+    steps = args.steps
+    for i in range(max(args.warmup, 1) if steps > 0 else 0):
+        step(i)
+    t0 = time.perf_counter()
+    budget = 150.0
+    done = 0
+    for i in range(steps):
+        step(i)
+        done += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    dt = time.perf_counter() - t0
+    value = done * sample / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.arch} 3x{args.target}x{args.target} synthetic IFCB ROIs, batch {args.batch}",
+                   "arch": args.arch, "batch": args.batch, "target": args.target,
+                   "note": "CPU arm: oracle port of the reference path (numpy cv2-exact transform + torch-CPU fp32 forward); "
+                           "the reference itself is Python and /root/reference does not travel to the GPU box"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{done} steps x {sample} ROIs of the batch", "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from sykepic_b200 import _lib, engine
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    args.batch = args.batch or (256 if args.arch == "resnet18" else 512)
+    dev = torch.device("cuda", local)
+
+    tmp = tempfile.mkdtemp(prefix=f"spk_bench_r{rank}_")
+    mdir = model_dir(args, tmp)
+    eng = engine.Engine(mdir, device=local, precision=args.precision, max_batch=args.batch, conv_impl=args.conv_impl)
+    thr = {name: 0.5 for name in eng.spec.classes}
+    eng.set_thresholds(thr)
+    n_pool = 8
+    batches = workload(args, 2000 + 100 * rank, n_pool)
+    in_bytes = [int((b[0].astype(np.int64) * b[1]).sum()) for b in batches]
+    K = eng.k
+
+    # ---- device-resident inputs (value) and pinned host inputs (e2e)
+    stream = eng.stream
+    dev_in = []
+    with torch.cuda.stream(stream):
+        for w, h, start, roi in batches:
+            dev_in.append((torch.from_numpy(roi).to(dev), torch.from_numpy(start).to(dev), torch.from_numpy(w).to(dev),
+                           torch.from_numpy(h).to(dev), len(roi)))
+        probs = torch.empty((args.batch, K), dtype=torch.float32, device=dev)
+        label = torch.empty(args.batch, dtype=torch.int32, device=dev)
+        cls = torch.empty(args.batch, dtype=torch.uint8, device=dev)
+        flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream.synchronize()
+
+    def step_device(i):
+        roi_d, start_d, w_d, h_d, roi_len = dev_in[i % n_pool]
+        eng.run_bin_device(roi_d, roi_len, start_d, w_d, h_d, args.batch, probs, label, cls)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, flush_l2=True):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with torch.cuda.stream(stream):
+            for i in range(steps):
+                if flush_l2:
+                    flush.zero_()  # evict L2 between steps, outside the timed events
+                evs[i][0].record(stream)
+                fn(i)
+                evs[i][1].record(stream)
+        stream.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step_device(i)
+    launches0 = eng.launches
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    ms_total = timed(step_device, args.steps)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    gpu_launches = eng.launches - launches0
+    assert eng.fault_count() == 0
+
+    # ---- e2e: host API, pinned host buffers, H2D + D2H inside the timed region
+    host_in = [(w, h, start, torch.from_numpy(roi).pin_memory().numpy()) for w, h, start, roi in batches]
+    ids = np.arange(args.batch, dtype=np.int32)
+
+    def step_host(i):
+        w, h, start, roi = host_in[i % n_pool]
+        eng.run_rois(ids, w, h, start, roi, want_labels=True)
+
+    for i in range(args.warmup):
+        step_host(i)
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d = int(np.mean(in_bytes)) + args.batch * 16
+    d2h = args.batch * (K * 4 + 4 + 1)
+
+    # ---- roofline pass: per-launch CUDA events on the engine's stream (separate pass, same inputs)
+    prof_steps = max(3, min(10, args.steps))
+    eng.profile_begin()
+    with torch.cuda.stream(stream):
+        for i in range(prof_steps):
+            flush.zero_()
+            step_device(i)
+    prof = eng.profile_read(detail=True)
+    eng.profile_end()
+    detail = prof.pop("detail")
+    if args.profile_detail and rank == 0:
+        agg = {}
+        for cat, ms, fl, by, what in detail:
+            a = agg.setdefault((cat, what), [0, 0.0, fl, by])
+            a[0] += 1
+            a[1] += ms
+        with open(args.profile_detail, "w") as fh:
+            fh.write("category\tlaunches\tavg_ms\tTFLOP/s\tGB/s(algorithmic)\twhat\n")
+            for (cat, what), (cnt, ms, fl, by) in agg.items():
+                avg = ms / cnt
+                fh.write(f"{cat}\t{cnt}\t{avg:.4f}\t{fl / avg / 1e9:.1f}\t{by / avg / 1e6:.1f}\t{what}\n")
+
+    # ---- reduce over ranks: max time
+    t = torch.tensor([ms_total, e2e_s, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s, wall = t.tolist()
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        step_ms = {c: v["ms"] / prof_steps for c, v in prof.items()}
+        total_prof_ms = sum(step_ms.values())
+        tc = prof.get("conv_tc")
+        mean_in = float(np.mean(in_bytes))
+        if tc:
+            ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12
+            peak = float(pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"])
+            roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM convolutions, all launches of a step)",
+                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "peak_kind": f"{pk_kind} bf16 sustained (cuBLAS)", "traffic": None,
+                        "launches_per_step": tc["launches"] // prof_steps, "share_of_step": step_ms["conv_tc"] / total_prof_ms}
+        else:
+            cs = prof.get("conv_simt", {"flops": 0.0, "ms": 1.0, "launches": 0})
+            ach = cs["flops"] / (cs["ms"] * 1e-3) / 1e12
+            peak = float(pk["bf16_tflops"])
+            roofline = {"bound": "tensor", "kernel": "conv_simt_kernel (CUDA-core FFMA; no tensor-core path in this precision)",
+                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_kind": pk_kind, "traffic": None}
+        pre = prof.get("preprocess")
+        pre_roof = None
+        if pre:
+            pre_bytes = pre["bytes"] + mean_in * pre["launches"]
+            g = pre_bytes / (pre["ms"] * 1e-3) / 1e9
+            pre_roof = {"bound": "hbm", "kernel": "preprocess_kernel", "achieved": g, "peak": float(pk["hbm_gbs"]), "unit": "GB/s",
+                        "frac": g / float(pk["hbm_gbs"]), "bytes_per_roi": pre_bytes / (pre["launches"] * args.batch)}
+        value = args.gpus * args.batch * args.steps / (ms_total * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"{args.arch} 3x{args.target}x{args.target} synthetic IFCB ROIs, batch {args.batch} per GPU, "
+                                   f"{args.precision}, random-init weights",
+                       "arch": args.arch, "batch_per_gpu": args.batch, "target": args.target, "conv_impl": args.conv_impl,
+                       "parallelism": f"bins sharded over {args.gpus} GPU(s), no collective",
+                       "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                       "mean_roi_bytes": mean_in / args.batch,
+                       "conv_gflop_per_roi_logical": CONV_GFLOP.get(args.arch) if args.target == 224 else None},
+            "e2e": {"value": args.gpus * args.batch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "api": "Engine.run_rois (host numpy/pinned in, host numpy out)"},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_preprocess": pre_roof,
+            "kernel_ms_per_step": step_ms,
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline:
+            rate, n_done, cores = cpu_port_rate(args, mdir, batches, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_done} ROIs of the same synthetic batch (oracle: numpy transform + torch-CPU fp32 forward)",
+                                    "host_cpus": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

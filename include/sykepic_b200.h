@@ -66,6 +66,21 @@ const char* spk_last_error(const spk_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t spk_launch_count(const spk_ctx* ctx);
 
+/* ---- per-kernel timing (bench.py's roofline leg) -------------------------------------------------
+ * While profiling is on, every launch of spk_preprocess / spk_forward is bracketed by CUDA events on
+ * the context's stream.  spk_profile_read synchronises, sums the elapsed time, the algorithmic FLOPs
+ * and the algorithmic bytes of the launches recorded since spk_profile_begin per category
+ * (SPK_PROF_*), and, when `detail` is not NULL, writes one text line per launch
+ * ("<category> <ms> <flops> <bytes> <description>\n") into it.  Profiling is off by default and
+ * costs nothing then. */
+enum { SPK_PROF_PREPROCESS = 0, SPK_PROF_CONV_TC = 1, SPK_PROF_CONV_SIMT = 2, SPK_PROF_STEM = 3,
+       SPK_PROF_POOL = 4, SPK_PROF_BN_RELU = 5, SPK_PROF_HEAD = 6, SPK_PROF_CATEGORIES = 8 };
+int spk_profile_begin(spk_ctx* ctx);
+int spk_profile_read(spk_ctx* ctx, double ms[SPK_PROF_CATEGORIES], double flops[SPK_PROF_CATEGORIES],
+                     double bytes[SPK_PROF_CATEGORIES], int64_t launches[SPK_PROF_CATEGORIES],
+                     char* detail, int64_t detail_cap);
+int spk_profile_end(spk_ctx* ctx);
+
 /* ---- A2: .adc parsing (host) ---------------------------------------------------------
  * Replaces the per-line parsing in sykepic/utils/ifcb.py:101-110 (raw_to_png) and
  * :133-145 (next_roi): ROI id = 1-based LINE number, width/height/start = comma fields

@@ -26,6 +26,7 @@ LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
 INT32_MAX = 2**31 - 1
+PROF_CATEGORIES = ["preprocess", "conv_tc", "conv_simt", "stem", "pool", "bn_relu", "head", "other"]
 
 
 class SpkError(RuntimeError):
@@ -62,6 +63,9 @@ PROTOTYPES = {
     "spk_synchronize": (_i, [_p]),
     "spk_last_error": (C.c_char_p, [_p]),
     "spk_launch_count": (_i64, [_p]),
+    "spk_profile_begin": (_i, [_p]),
+    "spk_profile_read": (_i, [_p, _p, _p, _p, _p, _p, _i64]),
+    "spk_profile_end": (_i, [_p]),
     "spk_adc_parse": (_i, [C.c_char_p, _i64, _i64, _p, _p, _p, _p, C.POINTER(_i64), C.POINTER(_i64)]),
     "spk_rois_validate": (_i, [_p, _p, _p, _i64, _i64, _i, _i, C.POINTER(_i64)]),
     "spk_new_dims": (None, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),

@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             *reinterpret_cast<uint4*>(yrow + c + j) = o;
           }
         }
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
       }
       tc_fence_before();
       __syncwarp();
@@ -501,6 +502,18 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
       return fail(ctx, SPK_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
     }
   }
+  // opt in to the large dynamic shared memory on THIS device (the attribute is per device)
+  cudaError_t ea = cudaSuccess;
+  switch (p->bn) {
+    case 256: ea = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmem); break;
+    case 128: ea = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmem); break;
+    case 64: ea = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem); break;
+    case 32: ea = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::kSmem); break;
+  }
+  if (ea != cudaSuccess) {
+    tc_conv_plan_destroy(p);
+    return fail(ctx, SPK_ERR_CUDA, "tcgen05 convolution: cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
+  }
   *out = p;
   return SPK_OK;
 }
@@ -516,11 +529,6 @@ int64_t tc_conv_plan_bytes(const TcConvPlan* p) { return p ? p->bytes : 0; }
 template <int BN>
 static int launch_bn(spk_ctx* ctx, const TcParams& prm) {
   using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    configured = true;
-  }
   const int grid = std::min(prm.total_tiles, ctx->sm_count);
   conv_tc_kernel<BN><<<grid, kThreads, C::kSmem, ctx->stream>>>(prm);
   SPK_LAUNCH_CHECK(ctx);

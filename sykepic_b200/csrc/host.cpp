@@ -27,6 +27,28 @@ int fail(spk_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+ProfScope::ProfScope(spk_ctx* c, int category, double flops, double bytes, const char* fmt, ...) : ctx(c) {
+  if (!c || !c->profiling) return;
+  ProfRec r;
+  r.category = category;
+  r.flops = flops;
+  r.bytes = bytes;
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  r.what = buf;
+  if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+  cudaEventRecord(r.start, c->stream);
+  idx = (int)c->prof.size();
+  c->prof.push_back(r);
+}
+
+ProfScope::~ProfScope() {
+  if (idx >= 0) cudaEventRecord(ctx->prof[(size_t)idx].stop, ctx->stream);
+}
+
 namespace {
 
 inline bool py_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r') || (c >= 0x1c && c <= 0x1f); }
@@ -69,6 +91,58 @@ using namespace spk;
 extern "C" {
 
 int spk_abi_version(void) { return SPK_ABI_VERSION; }
+
+static void prof_clear(spk_ctx* ctx) {
+  for (auto& r : ctx->prof) {
+    cudaEventDestroy(r.start);
+    cudaEventDestroy(r.stop);
+  }
+  ctx->prof.clear();
+}
+
+int spk_profile_begin(spk_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_profile_begin: null context");
+  prof_clear(ctx);
+  ctx->profiling = true;
+  return SPK_OK;
+}
+
+int spk_profile_end(spk_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_profile_end: null context");
+  cudaStreamSynchronize(ctx->stream);
+  prof_clear(ctx);
+  ctx->profiling = false;
+  return SPK_OK;
+}
+
+int spk_profile_read(spk_ctx* ctx, double ms[SPK_PROF_CATEGORIES], double flops[SPK_PROF_CATEGORIES],
+                     double bytes[SPK_PROF_CATEGORIES], int64_t launches[SPK_PROF_CATEGORIES], char* detail,
+                     int64_t detail_cap) {
+  if (!ctx || !ms || !flops || !bytes || !launches) return fail(ctx, SPK_ERR_INVALID, "spk_profile_read: bad arguments");
+  SPK_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < SPK_PROF_CATEGORIES; ++i) {
+    ms[i] = flops[i] = bytes[i] = 0.0;
+    launches[i] = 0;
+  }
+  int64_t pos = 0;
+  if (detail && detail_cap > 0) detail[0] = 0;
+  for (auto& r : ctx->prof) {
+    float t = 0.f;
+    SPK_CUDA_OK(ctx, cudaEventElapsedTime(&t, r.start, r.stop));
+    const int c = (r.category >= 0 && r.category < SPK_PROF_CATEGORIES) ? r.category : SPK_PROF_CATEGORIES - 1;
+    ms[c] += t;
+    flops[c] += r.flops;
+    bytes[c] += r.bytes;
+    launches[c] += 1;
+    if (detail && pos < detail_cap - 1) {
+      int m = snprintf(detail + pos, (size_t)(detail_cap - pos), "%d %.6f %.6g %.6g %s\n", c, (double)t, r.flops, r.bytes,
+                       r.what.c_str());
+      if (m > 0) pos += (m < detail_cap - pos) ? m : (detail_cap - pos - 1);
+    }
+  }
+  prof_clear(ctx);
+  return SPK_OK;
+}
 
 const char* spk_last_error(const spk_ctx* ctx) { return ctx ? ctx->error.c_str() : tls_error().c_str(); }
 

@@ -16,7 +16,7 @@
 
 namespace spk {
 
-enum OpKind { kOpConv = 0, kOpMaxPool = 1, kOpAvgPool = 2, kOpBnRelu = 3 };
+enum OpKind { kOpConv = 0, kOpMaxPool = 1, kOpAvgPool = 2, kOpBnRelu = 3, kOpStemPool = 4, kOpNop = 5 };
 
 struct Buffer {
   bool known = false;
@@ -37,6 +37,8 @@ struct Op {
   float* d_bias = nullptr; // conv: folded bias [Cout]; bn_relu: shift [C]
   float* d_scale = nullptr;  // bn_relu: scale [C]
   TcConvPlan* tc = nullptr;
+  uint4* d_stem_w = nullptr;  // fused stem: swizzled bf16 weight tile
+  int pool_out = -1, hp = 0, wp = 0, pool_ld = 0;  // fused stem: the max-pool's output
   std::vector<float> w_host;  // [Cout][kh][kw][cin] folded fp32, kept until net_end for the tcgen05 packer
   std::vector<float> b_host;
   int k = 0, stride = 0, pad = 0, channels = 0, relu = 0;
@@ -66,6 +68,7 @@ static void net_free(Net* net) {
     if (op.d_w) cudaFree(op.d_w);
     if (op.d_bias) cudaFree(op.d_bias);
     if (op.d_scale) cudaFree(op.d_scale);
+    if (op.d_stem_w) cudaFree(op.d_stem_w);
     if (op.tc) tc_conv_plan_destroy(op.tc);
   }
   if (net->d_head_w) cudaFree(net->d_head_w);
@@ -493,6 +496,37 @@ int spk_net_end(spk_ctx* ctx) {
   }
   SPK_CUDA_OK(ctx, cudaMalloc(&net->d_logits, (size_t)net->max_batch * net->classes * sizeof(float)));
   net->bytes += (int64_t)net->max_batch * net->classes * 4;
+  // ---- stem fusion: conv 7x7/2 on the u8 input followed by max-pool 3x3/2 -> one tcgen05 kernel
+  if (net->precision == SPK_PRECISION_BF16 && net->ops.size() >= 2) {
+    Op& c0 = net->ops[0];
+    Op& m1 = net->ops[1];
+    // is the conv output read by anything but the pool before its buffer id is written again?
+    bool other_reader = false;
+    for (size_t i = 2; i < net->ops.size(); ++i) {
+      if (net->ops[i].in == c0.out || net->ops[i].res == c0.out) {
+        other_reader = true;
+        break;
+      }
+      if (net->ops[i].out == c0.out) break;  // recycled id: overwritten first
+    }
+    if (c0.kind == kOpConv && c0.in == 0 && net->bufs[0].dtype == SPK_DTYPE_U8 && c0.impl != SPK_CONV_SIMT &&
+        m1.kind == kOpMaxPool && m1.in == c0.out && c0.res < 0 && c0.out_off == 0 && net->head_in != c0.out &&
+        stem_pool_supported(c0.g, m1.k, m1.stride, m1.pad) && (m1.g.ldy % 8) == 0 && !other_reader) {
+      rc = stem_pool_pack_weights(ctx, c0.w_host.data(), &c0.d_stem_w);
+      if (rc) return rc;
+      net->bytes += 16384;
+      rc = upload(ctx, c0.b_host.data(), c0.b_host.size(), &c0.d_bias);
+      if (rc) return rc;
+      c0.kind = kOpStemPool;
+      c0.pool_out = m1.out;
+      c0.hp = m1.g.ho;
+      c0.wp = m1.g.wo;
+      c0.pool_ld = m1.g.ldy;
+      m1.kind = kOpNop;
+      std::vector<float>().swap(c0.w_host);
+      std::vector<float>().swap(c0.b_host);
+    }
+  }
   for (auto& op : net->ops) {
     if (op.kind != kOpConv) continue;
     const ConvGeom& g = op.g;
@@ -551,6 +585,13 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
       case kOpConv: {
         ConvGeom g = op.g;
         g.n = (int)n;
+        const double px = (double)n * g.ho * g.wo;
+        ProfScope prof(ctx, op.in == 0 ? SPK_PROF_STEM : (op.impl == SPK_CONV_TCGEN05 ? SPK_PROF_CONV_TC : SPK_PROF_CONV_SIMT),
+                       2.0 * px * g.cout * g.kh * g.kw * g.cin,
+                       (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * (op.res >= 0 ? 2 : 1) +
+                           (double)g.cout * g.kh * g.kw * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
+                       "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
+                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "");
         const void* res = op.res >= 0 ? ptr(op.res, 0) : nullptr;
         if (op.impl == SPK_CONV_TCGEN05)
           rc = tc_conv_launch(ctx, op.tc, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
@@ -559,24 +600,48 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
                                 bo.dtype);
         break;
       }
-      case kOpMaxPool:
+      case kOpNop:
+        break;
+      case kOpStemPool: {
+        const ConvGeom& g = op.g;
+        const Buffer& bp = net->bufs[(size_t)op.pool_out];
+        ProfScope prof(ctx, SPK_PROF_STEM, 2.0 * n * g.ho * g.wo * g.cout * 49.0,
+                       (double)n * g.h * g.w + (double)n * op.hp * op.wp * g.cout * 2.0,
+                       "stem conv7x7/2 1->64 + relu + maxpool3/2 fused, in %dx%d out %dx%d n=%d", g.h, g.w, op.hp, op.wp, (int)n);
+        rc = launch_stem_pool(ctx, (int)n, g.h, g.w, (const uint8_t*)x, op.d_stem_w, op.d_bias, (__nv_bfloat16*)bp.d, g.ho,
+                              g.wo, op.hp, op.wp, op.pool_ld);
+        break;
+      }
+      case kOpMaxPool: {
+        ProfScope prof(ctx, SPK_PROF_POOL, 0.0, (double)n * ((double)op.g.h * op.g.w + (double)op.g.ho * op.g.wo) * op.g.cin * dtype_size(bo.dtype),
+                       "maxpool%d/%d c=%d in %dx%d n=%d", op.k, op.stride, op.g.cin, op.g.h, op.g.w, (int)n);
         rc = launch_maxpool(ctx, (int)n, op.g.h, op.g.w, op.g.cin, op.k, op.stride, op.pad, op.g.ho, op.g.wo, op.g.ldy,
                             ptr(op.in, 0), ptr(op.out, 0), bo.dtype);
         break;
-      case kOpAvgPool:
+      }
+      case kOpAvgPool: {
+        ProfScope prof(ctx, SPK_PROF_POOL, 0.0, (double)n * ((double)op.g.h * op.g.w + (double)op.g.ho * op.g.wo) * op.g.cin * dtype_size(bo.dtype),
+                       "avgpool%d/%d c=%d in %dx%d n=%d", op.k, op.stride, op.g.cin, op.g.h, op.g.w, (int)n);
         rc = launch_avgpool(ctx, (int)n, op.g.h, op.g.w, op.g.cin, op.g.ldx, op.k, op.stride, op.g.ho, op.g.wo, op.g.ldy,
                             ptr(op.in, 0), ptr(op.out, 0), bo.dtype);
         break;
-      case kOpBnRelu:
+      }
+      case kOpBnRelu: {
+        ProfScope prof(ctx, SPK_PROF_BN_RELU, 0.0, 2.0 * n * op.g.h * op.g.w * op.channels * dtype_size(bo.dtype),
+                       "bn_relu c=%d %dx%d n=%d", op.channels, op.g.h, op.g.w, (int)n);
         rc = launch_affine_relu(ctx, (long long)n * op.g.h * op.g.w, op.channels, op.g.ldx, op.d_scale, op.d_bias,
                                 ptr(op.in, 0), ptr(op.out, 0), bo.dtype, op.relu);
         break;
+      }
       default:
         rc = fail(ctx, SPK_ERR_STATE, "spk_forward: unknown op");
     }
     if (rc) return rc;
   }
   const Buffer& bh = net->bufs[(size_t)net->head_in];
+  ProfScope prof(ctx, SPK_PROF_HEAD, 2.0 * n * net->feat * net->classes,
+                 (double)n * bh.h * bh.w * net->feat * dtype_size(bh.dtype) + (double)n * net->classes * 4,
+                 "head pool %dx%d f=%d k=%d n=%d", bh.h, bh.w, net->feat, net->classes, (int)n);
   return launch_head(ctx, bh.d, bh.dtype, n, bh.h * bh.w, net->feat, net->d_head_w, net->d_head_b, net->classes,
                      softmax_scale, thr_q, net->d_logits, probs, label, classified);
 }

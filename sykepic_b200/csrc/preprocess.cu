@@ -397,6 +397,10 @@ extern "C" int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t ro
   p.out = out;
   p.faults = ctx->d_faults;
   p.slabs = 4;
+  const double out_bytes = (double)n * target_h * target_w * channels * (out_dtype == SPK_DTYPE_F32 ? 4 : out_dtype == SPK_DTYPE_BF16 ? 2 : 1);
+  // input bytes are data dependent (sum of w*h); the caller adds them -- recorded here: descriptors + output
+  ProfScope prof(ctx, SPK_PROF_PREPROCESS, 0.0, out_bytes + 16.0 * n, "preprocess T=%dx%d c=%d dtype=%d n=%lld", target_h, target_w,
+                 channels, out_dtype, (long long)n);
   const long long blocks = n * p.slabs;
   if (blocks > 0x7fffffffLL) return fail(ctx, SPK_ERR_UNSUPPORTED, "spk_preprocess: batch too large");
   preprocess_kernel<<<(unsigned)blocks, kThreads, kHBytes, ctx->stream>>>(p);

@@ -20,6 +20,16 @@ struct Net;  // net.cu
 
 }  // namespace spk
 
+namespace spk {
+// one timed launch (profiling mode only): CUDA events on the context's stream around the launch
+struct ProfRec {
+  int category;
+  cudaEvent_t start, stop;
+  double flops, bytes;
+  std::string what;
+};
+}  // namespace spk
+
 struct spk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -29,6 +39,8 @@ struct spk_ctx {
   float* d_default_lut = nullptr;          // 3*256: v/255 (true fp32 division)
   spk::Net* net = nullptr;
   int sm_count = 148;
+  bool profiling = false;
+  std::vector<spk::ProfRec> prof;
 };
 
 namespace spk {
@@ -37,6 +49,14 @@ namespace spk {
 std::string& tls_error();
 
 int fail(spk_ctx* ctx, int code, const char* fmt, ...);
+
+// profiling scope: records events around the launches issued while it lives (no-op unless ctx->profiling)
+struct ProfScope {
+  spk_ctx* ctx;
+  int idx = -1;
+  ProfScope(spk_ctx* c, int category, double flops, double bytes, const char* fmt, ...);
+  ~ProfScope();
+};
 
 #define SPK_CUDA_OK(ctx, expr)                                                              \
   do {                                                                                      \
@@ -101,8 +121,10 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y);
 int64_t tc_conv_plan_bytes(const TcConvPlan* p);
-// stem.cu: conv 7x7/2 (1 input plane) + bias + ReLU + maxpool 3x3/2, u8 in -> bf16 NHWC out
-int launch_stem_u8(spk_ctx* ctx, int n, int t_h, int t_w, const uint8_t* x, const float* lut256, const float* w_k64 /*[49][64]*/,
-                   const float* bias, __nv_bfloat16* y, int hp, int wp);
+// stem.cu: conv 7x7/2 (1 gray plane -> 64) + bias + ReLU + maxpool 3x3/2 fused on tcgen05; u8 in -> bf16 NHWC out
+bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int pool_pad);
+int stem_pool_pack_weights(spk_ctx* ctx, const float* w_folded /*[64][7][7]*/, uint4** d_out);
+int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, const uint4* w_sw, const float* bias,
+                     __nv_bfloat16* y, int hc, int wc, int hp, int wp, int ldy);
 
 }  // namespace spk

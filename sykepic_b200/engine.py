@@ -279,19 +279,20 @@ class Engine:
         `thresholds`: dict name -> float (classes without an entry can never be "classified"),
         a number (scalar rule: idxmax, classified iff p > thr) or None."""
         torch = self.torch
-        self._thr_scalar_q = None
         if thresholds is None:
             self._thr_dev = None
             return
         if isinstance(thresholds, (int, float)):
-            self._thr_scalar_q = int(self.lib.spk_threshold_quantize(float(thresholds), 1))
-            self._thr_dev = None
-            return
-        q = np.full(self.k, _lib.INT32_MAX, np.int32)
-        for i, name in enumerate(self.spec.classes):
-            if name in thresholds:
-                q[i] = self.lib.spk_threshold_quantize(float(thresholds[name]), 0)
-        self._thr_dev = torch.from_numpy(q).to(self.device)
+            # scalar rule (prediction.py:57-59): (idxmax, p > thr) == "best class strictly above thr"
+            q = np.full(self.k, int(self.lib.spk_threshold_quantize(float(thresholds), 1)), np.int32)
+        else:
+            q = np.full(self.k, _lib.INT32_MAX, np.int32)
+            for i, name in enumerate(self.spec.classes):
+                if name in thresholds:
+                    q[i] = self.lib.spk_threshold_quantize(float(thresholds[name]), 0)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self._thr_dev = torch.from_numpy(q).to(self.device)
+        self.stream.synchronize()
 
     # ------------------------------------------------------------------ device steps
     def preprocess(self, roi_dev, roi_len, start_dev, w_dev, h_dev, n, out, out_dtype=_lib.DTYPE_U8, channels=1,
@@ -306,6 +307,50 @@ class Engine:
         """K2 + K3 on a preprocessed u8 batch [n, T, T]."""
         self._ck(self.lib.spk_forward(self.ctx, ptr(x_u8), n, self.softmax_scale, ptr(self._thr_dev), ptr(probs_out),
                                       ptr(label_out), ptr(classified_out)))
+
+    def last_logits(self, n):
+        """Logits [n, K] of the last `forward` (host copy; test / debug tap)."""
+        addr = self.lib.spk_last_logits(self.ctx)
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n, self.k), "typestr": "<f4", "data": (addr, False), "version": 2}
+
+        self.synchronize()
+        with self.torch.cuda.device(self.device):
+            return self.torch.as_tensor(_Raw(), device=self.device).cpu().numpy().copy()
+
+    def read_buffer(self, buf, n):
+        """Activation buffer `buf` of the last forward as float32 [n, h, w, c] (test / debug tap)."""
+        h, w, c = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.spk_net_read_buffer(self.ctx, buf, n, None, 0, C.byref(h), C.byref(w), C.byref(c)))
+        out = np.empty((n, h.value, w.value, c.value), np.float32)
+        self._ck(self.lib.spk_net_read_buffer(self.ctx, buf, n, ptr(out), out.size, C.byref(h), C.byref(w), C.byref(c)))
+        return out
+
+    # ------------------------------------------------------------------ per-kernel timing
+    def profile_begin(self):
+        self._ck(self.lib.spk_profile_begin(self.ctx))
+
+    def profile_read(self, detail=False):
+        """-> {category: {"ms", "flops", "bytes", "launches"}} (+ "detail": list of per-launch tuples)."""
+        n = len(_lib.PROF_CATEGORIES)
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        la = (C.c_int64 * n)()
+        cap = 1 << 20 if detail else 0
+        buf = C.create_string_buffer(cap) if detail else None
+        self._ck(self.lib.spk_profile_read(self.ctx, ms, fl, by, la, buf, cap))
+        out = {name: {"ms": ms[i], "flops": fl[i], "bytes": by[i], "launches": int(la[i])}
+               for i, name in enumerate(_lib.PROF_CATEGORIES) if la[i]}
+        if detail:
+            rows = []
+            for line in buf.value.decode().splitlines():
+                c, t, f, b, what = line.split(" ", 4)
+                rows.append((_lib.PROF_CATEGORIES[int(c)], float(t), float(f), float(b), what))
+            out["detail"] = rows
+        return out
+
+    def profile_end(self):
+        self._ck(self.lib.spk_profile_end(self.ctx))
 
     def fault_count(self):
         v = C.c_int64()

@@ -1,0 +1,159 @@
+"""K2 + K3 (convolutions, head, softmax, thresholds) and the whole `sykepic prob` path on the GPU,
+against what the REFERENCE produced on the same bins and checkpoints (tests/golden).
+
+Tolerances (BASELINE.json north_star): FP32 probabilities within 1e-4 absolute, BF16 within 2e-2,
+thresholded labels agree on >= 99.9 % of ROIs (FP32)."""
+
+import json
+
+import numpy as np
+import pytest
+
+from oracle import prediction as o_pred
+from sykepic_b200 import engine, synth
+from sykepic_b200.compute import prediction, probability
+from tests.cases import CASES, FIXTURE, GOLDEN, case_bins
+
+pytestmark = pytest.mark.gpu
+
+FP32_PROB_TOL = 1e-4
+BF16_PROB_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def engines(model_dirs):
+    cache = {}
+
+    def get(case, precision, impl="auto", max_batch=64):
+        key = (case, precision, impl, max_batch)
+        if key not in cache:
+            cache[key] = engine.Engine(model_dirs(case), precision=precision, conv_impl=impl, max_batch=max_batch)
+        return cache[key]
+
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+def _thresholds(tname):
+    return 0.5 if tname.startswith("scalar") else o_pred.threshold_dictionary(FIXTURE / f"{tname}.txt")
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fp32_probabilities_and_labels(engines, case):
+    eng = engines(case, "fp32")
+    labels = json.loads((GOLDEN / f"case_{case}.labels.json").read_text())
+    total = agree = 0
+    for bname, b in case_bins(case):
+        g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+        for tname in ("thresholds-2021", "thresholds-zero", "scalar-0.5"):
+            eng.set_thresholds(_thresholds(tname))
+            rid, probs, label, classified = eng.run_bin(b["adc_text"], b["roi_bytes"], want_labels=True)
+            assert rid.tolist() == g["roi_id"].tolist()
+            assert np.abs(probs - g["probs"]).max() <= FP32_PROB_TOL
+            logits = eng.last_logits(len(rid))
+            scale = max(1.0, float(np.abs(g["logits"]).max()))
+            assert np.abs(logits - g["logits"]).max() <= 2e-4 * scale
+            # the fused label rule == the host rule on the CSV decimals of the same probabilities
+            vals = o_pred.parse_prob_csv_text(engine.format_prob_csv(eng.spec.classes, rid, probs).decode())[2]
+            idx, flag = prediction.predict_array(vals, eng.spec.classes, _thresholds(tname))
+            assert label.tolist() == idx.tolist() and classified.tolist() == flag.tolist()
+            # ... and agrees with the labels the reference derived from ITS OWN csv
+            want = labels[bname][tname]
+            names = [eng.spec.classes[i] for i in label]
+            same = [(a == b2 and bool(c) == d) for a, b2, c, d in zip(names, want["prediction"], classified, want["classified"])]
+            total += len(same)
+            agree += sum(same)
+    assert total > 0 and agree / total >= 0.999, (agree, total)
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_bf16_probabilities(engines, case):
+    eng = engines(case, "bf16")
+    eng.set_thresholds(_thresholds("thresholds-zero"))
+    labels = json.loads((GOLDEN / f"case_{case}.labels.json").read_text())
+    total = agree = 0
+    for bname, b in case_bins(case):
+        g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+        rid, probs, label, classified = eng.run_bin(b["adc_text"], b["roi_bytes"], want_labels=True)
+        assert np.isfinite(probs).all()
+        assert np.abs(probs - g["probs"]).max() <= BF16_PROB_TOL, float(np.abs(probs - g["probs"]).max())
+        want = labels[bname]["thresholds-zero"]["prediction"]
+        total += len(want)
+        agree += sum(eng.spec.classes[i] == n for i, n in zip(label, want))
+    assert agree / total >= 0.95, (agree, total)
+
+
+@pytest.mark.parametrize("case", ["r18_224n", "r50_224"])
+def test_tcgen05_and_cuda_core_paths_agree(engines, case):
+    """Whole network, bf16 activations: tensor-core path (bf16 weights, fused stem) against the CUDA-core
+    path (fp32 weights).  Both must sit inside the BF16 gate of the reference's probabilities; the tight
+    layer-by-layer comparison is tests/test_gpu_conv.py."""
+    tc = engines(case, "bf16", "auto")
+    simt = engines(case, "bf16", "simt")
+    bname, b = case_bins(case)[-1]
+    g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+    _, p_tc = tc.run_bin(b["adc_text"], b["roi_bytes"])
+    _, p_simt = simt.run_bin(b["adc_text"], b["roi_bytes"])
+    assert np.abs(p_tc - g["probs"]).max() <= BF16_PROB_TOL
+    assert np.abs(p_simt - g["probs"]).max() <= BF16_PROB_TOL
+    assert np.abs(p_tc - p_simt).max() <= 3e-2
+
+
+def test_batch_split_and_partial_batches(engines):
+    """Batches of 7 (ragged last batch) give the same probabilities as one batch."""
+    eng = engines("r18_180", "fp32")
+    bname, b = case_bins("r18_180")[2]
+    _, p_all = eng.run_bin(b["adc_text"], b["roi_bytes"])
+    _, p_7 = eng.run_bin(b["adc_text"], b["roi_bytes"], batch_size=7)
+    assert np.abs(p_all - p_7).max() <= 1e-6
+
+
+def test_prob_main_writes_reference_layout(engines, model_dirs, tmp_path):
+    """`probability.main` end to end: same relative path, header, ROI ids and (within 1e-4) values as the
+    CSV the reference wrote; existing CSV is skipped unless force; faulty / empty bins behave like the reference."""
+    case = "r18_180"
+    raw = tmp_path / "raw"
+    paths = [synth.write_bin(raw, bname, b) for bname, b in case_bins(case)]
+    # a truncated bin ("Faulty raw data": no CSV) and an empty bin (header-only CSV)
+    bad = case_bins(case)[1][1]
+    bad_path = synth.write_bin(raw, "D20210601T000000_IFCB114", {"adc_text": bad["adc_text"], "roi_bytes": bad["roi_bytes"][:-5]})
+    empty_path = synth.write_bin(raw, "D20210601T002000_IFCB114", {"adc_text": "", "roi_bytes": np.zeros(0, np.uint8)})
+    out = tmp_path / "out"
+    done = probability.main(paths + [bad_path, empty_path], model_dirs(case), out, batch_size=16, num_workers=2,
+                            force=False, progress_bar=False, precision="fp32")
+    assert done == {p.name for p in paths} | {empty_path.name}
+    labels = json.loads((GOLDEN / f"case_{case}.labels.json").read_text())
+    for p in paths:
+        rel = labels[p.name]["csv_relpath"]
+        got = o_pred.parse_prob_csv_text((out / rel).read_text())
+        want = o_pred.parse_prob_csv_text((GOLDEN / f"case_{case}__{p.name}.prob.csv").read_text())
+        assert got[0] == want[0] and got[1].tolist() == want[1].tolist()
+        assert np.abs(got[2] - want[2]).max() <= FP32_PROB_TOL + 1e-5
+    assert not list(out.glob(f"**/{bad_path.name}*"))
+    assert (out / "2021/06/01" / f"{empty_path.name}.prob.csv").read_text().count("\n") == 1
+    # skip / force
+    target = out / labels[paths[0].name]["csv_relpath"]
+    target.write_text("sentinel")
+    probability.main(paths[:1], model_dirs(case), out, 16, 2, False, progress_bar=False, precision="fp32")
+    assert target.read_text() == "sentinel"
+    probability.main(paths[:1], model_dirs(case), out, 16, 2, True, progress_bar=False, precision="fp32")
+    assert target.read_text().startswith("roi,")
+
+
+def test_cli_prob_then_class(model_dirs, tmp_path):
+    from sykepic_b200.__main__ import main as cli
+
+    case = "r18_180"
+    raw = tmp_path / "raw"
+    for bname, b in case_bins(case):
+        synth.write_bin(raw, bname, b)
+    out = tmp_path / "prob"
+    assert cli(["prob", "-r", str(raw), "-m", str(model_dirs(case)), "-o", str(out), "-b", "32"]) == 0
+    assert len(list(out.glob("**/*.prob.csv"))) == 3
+    thr = tmp_path / "thr.txt"
+    thr.write_text((FIXTURE / "thresholds-zero.txt").read_text() +
+                   "Dolichospermum-Anabaenopsis_coiled 0\nNodularia_spumigena-coiled 0\n")
+    assert cli(["class", str(out), "-t", str(thr), "-o", str(tmp_path / "class.csv")]) == 0
+    lines = (tmp_path / "class.csv").read_text().splitlines()
+    assert lines[0].startswith("Time,") and len(lines) == 4
