@@ -29,6 +29,23 @@ def _bf16(x):
     return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.bfloat16).float().numpy()
 
 
+def _bf16_diffused(w):
+    """The tensor-core packer's weight rounding (conv_tc.cu, tc_conv_plan_create): round to bf16 carrying the
+    rounding error into the next weight of the same output channel, input channel outer / tap inner."""
+    import torch
+
+    cout = w.shape[0]
+    flat = torch.from_numpy(np.ascontiguousarray(w, np.float32)).reshape(cout, -1).double()  # [o][(c, r, s)]
+    out = torch.empty_like(flat)
+    carry = torch.zeros(cout, dtype=torch.float64)
+    for k in range(flat.shape[1]):
+        want = flat[:, k] + carry
+        q = want.float().to(torch.bfloat16).double()
+        carry = want - q
+        out[:, k] = q
+    return out.float().reshape(w.shape).numpy()
+
+
 def run_net(ctx, img, w1, w2, stride, pad, relu, residual, impl, n, t):
     """u8 image [n,t,t] -> conv1 (3x3/1, 1->c1, ReLU, CUDA cores) -> conv2 (the layer under test)
     [-> + residual branch conv3 1x1 of the same input].  Returns (conv1 out, conv2 out) as fp32 NHWC."""
@@ -100,9 +117,9 @@ def test_tcgen05_conv_matches_cuda_cores_and_torch(ctx, t, n, c1, c2, k, stride,
     a_simt, y_simt, r_simt, bias = run_net(ctx, img, w1, w2, stride, pad, relu, wr, _lib.CONV_SIMT, n, t)
     a_tc, y_tc, r_tc, _ = run_net(ctx, img, w1, w2, stride, pad, relu, wr, _lib.CONV_TCGEN05, n, t)
     assert np.array_equal(a_simt, a_tc)  # same conv1 on both paths
-    # torch fp32 reference of conv2 on the SAME bf16 input and bf16-rounded weights
+    # torch fp32 reference of conv2 on the SAME bf16 input and the same (error-diffused) bf16 weights
     x = torch.from_numpy(a_tc).permute(0, 3, 1, 2)
-    ref = F.conv2d(x, torch.from_numpy(_bf16(w2)), torch.from_numpy(bias), stride=stride, padding=pad)
+    ref = F.conv2d(x, torch.from_numpy(_bf16_diffused(w2)), torch.from_numpy(bias), stride=stride, padding=pad)
     if residual:
         ref = ref + torch.from_numpy(r_tc).permute(0, 3, 1, 2)
     if relu:
