@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None, help="ROIs per step per GPU (default 256; 512 for resnet50/densenet121)")
     ap.add_argument("--target", type=int, default=224)
     ap.add_argument("--precision", choices=("bf16", "fp32"), default="bf16")
-    ap.add_argument("--conv-impl", choices=("auto", "simt", "tcgen05"), default="auto")
+    ap.add_argument("--conv-impl", choices=("auto", "simt", "tcgen05", "taps"), default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-detail", metavar="FILE", help="write the per-launch timing table of the roofline pass")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")

@@ -50,8 +50,10 @@ enum { SPK_BORDER_MODE = 0, SPK_BORDER_BLACK = 1, SPK_BORDER_WHITE = 2 }; /* syk
 enum { SPK_DTYPE_F32 = 0, SPK_DTYPE_BF16 = 1, SPK_DTYPE_U8 = 2 };
 enum { SPK_LAYOUT_NCHW = 0, SPK_LAYOUT_NHWC = 1 };
 enum { SPK_PRECISION_FP32 = 0, SPK_PRECISION_BF16 = 1 };
-/* implementation selector for convolutions in bf16 precision */
-enum { SPK_CONV_AUTO = 0, SPK_CONV_SIMT = 1, SPK_CONV_TCGEN05 = 2 };
+/* implementation selector for convolutions in bf16 precision: AUTO / TCGEN05 pick the halo-resident
+ * kernel for 3x3 stride-1 layers on large maps and the tap-per-TMA kernel elsewhere; TCGEN05_TAPS
+ * forces the tap-per-TMA kernel everywhere (A/B comparison). */
+enum { SPK_CONV_AUTO = 0, SPK_CONV_SIMT = 1, SPK_CONV_TCGEN05 = 2, SPK_CONV_TCGEN05_TAPS = 3 };
 
 typedef struct spk_ctx spk_ctx;
 

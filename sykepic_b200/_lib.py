@@ -24,7 +24,7 @@ BORDER = {"mode": 0, "black": 1, "white": 2}
 DTYPE_F32, DTYPE_BF16, DTYPE_U8 = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 PRECISION_FP32, PRECISION_BF16 = 0, 1
-CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
+CONV_AUTO, CONV_SIMT, CONV_TCGEN05, CONV_TCGEN05_TAPS = 0, 1, 2, 3
 INT32_MAX = 2**31 - 1
 PROF_CATEGORIES = ["preprocess", "conv_tc", "conv_simt", "stem", "pool", "bn_relu", "head", "other"]
 

@@ -37,6 +37,7 @@ struct Op {
   float* d_bias = nullptr; // conv: folded bias [Cout]; bn_relu: shift [C]
   float* d_scale = nullptr;  // bn_relu: scale [C]
   TcConvPlan* tc = nullptr;
+  HaloConvPlan* halo = nullptr;
   uint4* d_stem_w = nullptr;  // fused stem: swizzled bf16 weight tile
   int pool_out = -1, hp = 0, wp = 0, pool_ld = 0;  // fused stem: the max-pool's output
   std::vector<float> w_host;  // [Cout][kh][kw][cin] folded fp32, kept until net_end for the tcgen05 packer
@@ -70,6 +71,7 @@ static void net_free(Net* net) {
     if (op.d_scale) cudaFree(op.d_scale);
     if (op.d_stem_w) cudaFree(op.d_stem_w);
     if (op.tc) tc_conv_plan_destroy(op.tc);
+    if (op.halo) halo_conv_plan_destroy(op.halo);
   }
   if (net->d_head_w) cudaFree(net->d_head_w);
   if (net->d_head_b) cudaFree(net->d_head_b);
@@ -534,6 +536,8 @@ int spk_net_end(spk_ctx* ctx) {
     int impl = op.impl;
     const bool tc_ok = net->precision == SPK_PRECISION_BF16 && net->bufs[(size_t)op.in].dtype == SPK_DTYPE_BF16 &&
                        tc_conv_supported(g);
+    const bool taps_only = impl == SPK_CONV_TCGEN05_TAPS;
+    if (taps_only) impl = SPK_CONV_TCGEN05;
     if (impl == SPK_CONV_AUTO) impl = tc_ok ? SPK_CONV_TCGEN05 : SPK_CONV_SIMT;
     if (impl == SPK_CONV_TCGEN05 && !tc_ok)
       return fail(ctx, SPK_ERR_UNSUPPORTED, "spk_net_end: tcgen05 convolution does not support %dx%d s%d cin %d cout %d here",
@@ -544,9 +548,15 @@ int spk_net_end(spk_ctx* ctx) {
     if (impl == SPK_CONV_TCGEN05) {
       ConvGeom gm = g;
       gm.n = net->max_batch;
-      rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc);
-      if (rc) return rc;
-      net->bytes += tc_conv_plan_bytes(op.tc);
+      if (!taps_only && halo_conv_supported(gm)) {
+        rc = halo_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.halo);
+        if (rc) return rc;
+        net->bytes += halo_conv_plan_bytes(op.halo);
+      } else {
+        rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc);
+        if (rc) return rc;
+        net->bytes += tc_conv_plan_bytes(op.tc);
+      }
     } else {
       // SIMT layout: [K][Cout], K ordered (r, s, c)
       std::vector<float> wk((size_t)K * g.cout);
@@ -590,10 +600,12 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
                        2.0 * px * g.cout * g.kh * g.kw * g.cin,
                        (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * (op.res >= 0 ? 2 : 1) +
                            (double)g.cout * g.kh * g.kw * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
-                       "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
-                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "");
+                       "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
+                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.halo ? " [halo]" : "");
         const void* res = op.res >= 0 ? ptr(op.res, 0) : nullptr;
-        if (op.impl == SPK_CONV_TCGEN05)
+        if (op.halo)
+          rc = halo_conv_launch(ctx, op.halo, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
+        else if (op.impl == SPK_CONV_TCGEN05)
           rc = tc_conv_launch(ctx, op.tc, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
         else
           rc = launch_conv_simt(ctx, g, ptr(op.in, op.in_off), bi.dtype, op.d_w, op.d_bias, res, ptr(op.out, op.out_off),

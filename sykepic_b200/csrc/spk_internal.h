@@ -121,6 +121,14 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y);
 int64_t tc_conv_plan_bytes(const TcConvPlan* p);
+// conv_halo.cu (3x3 / stride 1: halo tile resident in shared memory, taps = shifted descriptors, TMA-store epilogue)
+struct HaloConvPlan;
+bool halo_conv_supported(const ConvGeom& g);
+int halo_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
+                          const float* bias, HaloConvPlan** out);
+void halo_conv_plan_destroy(HaloConvPlan* p);
+int halo_conv_launch(spk_ctx* ctx, HaloConvPlan* p, int n, const void* x, const void* res, void* y);
+int64_t halo_conv_plan_bytes(const HaloConvPlan* p);
 // stem.cu: conv 7x7/2 (1 gray plane -> 64) + bias + ReLU + maxpool 3x3/2 fused on tcgen05; u8 in -> bf16 NHWC out
 bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int pool_pad);
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w_folded /*[64][7][7]*/, uint4** d_out);

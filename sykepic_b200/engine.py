@@ -107,7 +107,7 @@ class Engine:
         self.device = torch.device("cuda", device)
         self.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
         self.precision_name = precision
-        self.conv_impl = {"auto": _lib.CONV_AUTO, "simt": _lib.CONV_SIMT, "tcgen05": _lib.CONV_TCGEN05}[conv_impl]
+        self.conv_impl = {"auto": _lib.CONV_AUTO, "simt": _lib.CONV_SIMT, "tcgen05": _lib.CONV_TCGEN05, "taps": _lib.CONV_TCGEN05_TAPS}[conv_impl]
         self.max_batch = int(max_batch)
         c, th, tw = spec.img_shape
         if c != 3:

@@ -29,23 +29,6 @@ def _bf16(x):
     return torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(torch.bfloat16).float().numpy()
 
 
-def _bf16_diffused(w):
-    """The tensor-core packer's weight rounding (conv_tc.cu, tc_conv_plan_create): round to bf16 carrying the
-    rounding error into the next weight of the same output channel, input channel outer / tap inner."""
-    import torch
-
-    cout = w.shape[0]
-    flat = torch.from_numpy(np.ascontiguousarray(w, np.float32)).reshape(cout, -1).double()  # [o][(c, r, s)]
-    out = torch.empty_like(flat)
-    carry = torch.zeros(cout, dtype=torch.float64)
-    for k in range(flat.shape[1]):
-        want = flat[:, k] + carry
-        q = want.float().to(torch.bfloat16).double()
-        carry = want - q
-        out[:, k] = q
-    return out.float().reshape(w.shape).numpy()
-
-
 def run_net(ctx, img, w1, w2, stride, pad, relu, residual, impl, n, t):
     """u8 image [n,t,t] -> conv1 (3x3/1, 1->c1, ReLU, CUDA cores) -> conv2 (the layer under test)
     [-> + residual branch conv3 1x1 of the same input].  Returns (conv1 out, conv2 out) as fp32 NHWC."""
@@ -101,11 +84,23 @@ GEOMS = [
     (23, 5, 64, 128, 3, 2, 1, True, True),      # odd size with stride 2
     (30, 2, 96, 32, 3, 1, 1, False, False),     # DenseNet-like: Cin not a multiple of 64, Cout = 32
     (16, 6, 160, 128, 1, 1, 0, True, False),    # DenseNet 1x1 with a 32-channel tail chunk
+    # halo-resident 3x3 kernel (conv_halo.cu): streamed weights shared by two M tiles, odd tile counts, clipped last rows
+    (28, 5, 128, 128, 3, 1, 1, True, True),     # ResNet-18 layer2: BN = 128, MT = 2, two k chunks, residual by TMA
+    (28, 7, 128, 64, 3, 1, 1, False, False),    # BN = 64 streamed, 49 M tiles (odd: the last pair is half empty)
+    (57, 3, 64, 64, 3, 1, 1, True, True),       # resident weights, H not a multiple of the tile rows (TMA store clips)
+    (30, 3, 64, 128, 3, 1, 1, True, False),     # Cin 64 -> Cout 128, 4-row tiles with a 2-row remainder
+    (28, 2, 64, 192, 3, 1, 1, True, True),      # three N tiles of 64
 ]
+HALO_GEOMS = [0, 1, 10, 12]  # also run through the tap-per-TMA kernel (SPK_CONV_TCGEN05_TAPS)
+
+
+@pytest.mark.parametrize("gi", HALO_GEOMS, ids=[f"g{i}" for i in HALO_GEOMS])
+def test_tap_kernel_on_halo_geometries(ctx, gi):
+    test_tcgen05_conv_matches_cuda_cores_and_torch(ctx, *GEOMS[gi], impl_tc=_lib.CONV_TCGEN05_TAPS)
 
 
 @pytest.mark.parametrize("t,n,c1,c2,k,stride,pad,relu,residual", GEOMS, ids=[f"g{i}" for i in range(len(GEOMS))])
-def test_tcgen05_conv_matches_cuda_cores_and_torch(ctx, t, n, c1, c2, k, stride, pad, relu, residual):
+def test_tcgen05_conv_matches_cuda_cores_and_torch(ctx, t, n, c1, c2, k, stride, pad, relu, residual, impl_tc=_lib.CONV_TCGEN05):
     import torch
     import torch.nn.functional as F
 
@@ -115,11 +110,11 @@ def test_tcgen05_conv_matches_cuda_cores_and_torch(ctx, t, n, c1, c2, k, stride,
     w2 = (rng.standard_normal((c2, c1, k, k)) * np.sqrt(2.0 / (c1 * k * k))).astype(np.float32)
     wr = (rng.standard_normal((c2, c1, 1, 1)) * np.sqrt(1.0 / c1)).astype(np.float32) if residual else None
     a_simt, y_simt, r_simt, bias = run_net(ctx, img, w1, w2, stride, pad, relu, wr, _lib.CONV_SIMT, n, t)
-    a_tc, y_tc, r_tc, _ = run_net(ctx, img, w1, w2, stride, pad, relu, wr, _lib.CONV_TCGEN05, n, t)
+    a_tc, y_tc, r_tc, _ = run_net(ctx, img, w1, w2, stride, pad, relu, wr, impl_tc, n, t)
     assert np.array_equal(a_simt, a_tc)  # same conv1 on both paths
-    # torch fp32 reference of conv2 on the SAME bf16 input and the same (error-diffused) bf16 weights
+    # torch fp32 reference of conv2 on the SAME bf16 input and bf16-rounded weights
     x = torch.from_numpy(a_tc).permute(0, 3, 1, 2)
-    ref = F.conv2d(x, torch.from_numpy(_bf16_diffused(w2)), torch.from_numpy(bias), stride=stride, padding=pad)
+    ref = F.conv2d(x, torch.from_numpy(_bf16(w2)), torch.from_numpy(bias), stride=stride, padding=pad)
     if residual:
         ref = ref + torch.from_numpy(r_tc).permute(0, 3, 1, 2)
     if relu:
