@@ -7,127 +7,94 @@
 // one (w' = sum_c w[:, c]) and ToTensor's 1/255 is folded into the weights, so the A operand is the
 // exact integer pixel value in bf16.
 //
-// One CTA = one image x one strip of 7 pooled rows.  GEMM per conv output row: M = 128 (the row's
-// <= 128 output columns), N = 64, K = 64 (k = 8 r + s; s = 7 and r = 7 carry zero weights).
-//   warps 0-3  build the A operand: gather the 7x8 input patch of every output column from the
-//              image strip staged in shared memory, convert u8 -> bf16 and store it in the K-major
-//              SWIZZLE_128B layout (3-stage ring);
+// One CTA = one image x one strip of 4 pooled rows (9 conv rows), two CTAs per SM.
+// GEMM per conv output row: M = 128 (the row's <= 128 output columns), K = 64 (k = 8 r + s; s = 7 and
+// r = 7 carry zero weights), N = 128 (the 64 output channels twice: bf16 hi and bf16 lo part of the
+// weight, w = hi + lo to 2^-17, summed in the epilogue -- the stem keeps fp32-weight accuracy).
+//
+// The A operand is never materialised per conv row.  For every INPUT row y the builder warps write
+//   E_y[j][0..8) = bf16(x[y][2j-3 .. 2j+5))        j = 0..127, 16 bytes each, 2 KB per input row,
+// once; conv row i then reads E_{2i-3} .. E_{2i+4} as the eight 16-byte K chunks of its operand through
+// a NO-SWIZZLE ("interleaved") K-major descriptor: rows 16 bytes apart, 8-row groups 128 bytes apart
+// (SBO), the two K chunks of an MMA one input row = 2048 bytes apart (LBO).  Each E row serves 3.5 conv
+// rows, so the u8 -> bf16 expansion costs 2 input rows per conv row instead of 7.
+//   warps 0-3  stage the u8 strip, build E rows (2 per step), signal one mbarrier per conv row;
 //   warp 4     allocates TMEM, issues tcgen05.mma (one thread), commits to mbarriers;
-//   warps 5-8  epilogue: tcgen05.ld the row's accumulator (4-slot TMEM ring), running vertical max
-//              of the 3 conv rows of a pooled row in registers, + bias, ReLU, bf16, horizontal max
-//              through shared memory, coalesced 16-byte stores of the pooled row.
+//   warps 5-8  epilogue: tcgen05.ld hi + lo, + bias, ReLU, bf16, running vertical max of the 3 conv
+//              rows of a pooled row as packed bf16x2 (max commutes with the monotone bias / ReLU /
+//              rounding), horizontal max through shared memory, coalesced 16-byte stores.
 // The 112x112x64 conv output (411 MB per 256 images in bf16) never exists in HBM.
 #include <cuda.h>
 
 #include <cstring>
 
 #include "spk_internal.h"
+#include "tc_common.cuh"
 
 namespace spk {
 namespace {
+using namespace tc;
 
 constexpr int kBuilders = 128;
-constexpr int kThreads = 288;  // 4 builder warps + 1 MMA warp + 4 epilogue warps
-constexpr int kAStages = 3;
-constexpr int kSlots = 4;      // TMEM accumulator ring: 4 x 64 columns
-constexpr int kABytes = 128 * 128;
-constexpr int kBTile = 64 * 128;
-constexpr int kBBytes = 2 * kBTile;  // weights as bf16 hi + bf16 lo tiles (w = hi + lo to 2^-17): two MMA passes over one A tile
+constexpr int kThreads = 288;           // 4 builder warps + 1 MMA warp + 4 epilogue warps
+constexpr int kSlots = 2;               // TMEM accumulator ring: 2 x 128 columns (two CTAs share the SM's 512)
+constexpr int kPoolRowsPerStrip = 4;
+constexpr int kMaxConvRows = 2 * kPoolRowsPerStrip + 1;
+constexpr int kSteps = kMaxConvRows + 3;  // builder steps (2 input rows each)
+constexpr int kERows = 2 * kSteps;        // E rows of a strip (the last one only meets zero weights)
+constexpr int kERowBytes = 128 * 16;      // one E row: 128 output columns x 8 bf16
+constexpr int kEBytes = kERows * kERowBytes;
+constexpr int kBBytes = 8 * 128 * 16;     // weights: 8 K chunks x (64 hi + 64 lo rows) x 8 bf16
 constexpr int kPoolBytes = 128 * 128;
-constexpr int kPoolRowsPerStrip = 7;
-constexpr int kMaxImgRows = 2 * (2 * kPoolRowsPerStrip + 1 - 1) + 7 + 1;  // input rows of a strip + slack
 constexpr int kMaxT = 256;
 constexpr int kPitchPad = 16;
 
 struct StemParams {
   const uint8_t* x;      // [n, th, tw] u8
-  const uint4* w_sw;     // 16 KB: the 64 x 64 bf16 weight tiles (hi, lo), already in the swizzled smem layout
+  const uint4* w_il;     // 16 KB: the weight tile in the interleaved (no-swizzle) K-major layout
   const float* bias;     // [64]
   __nv_bfloat16* y;      // [n, hp, wp, ldy]
   int n, th, tw, hc, wc, hp, wp, ldy;
-  int strips, m_count, pitch;
+  int strips, pitch;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+// no-swizzle K-major descriptor: rows 16 B apart inside an 8-row core matrix, SBO between core matrices
+// along M / N, LBO between the two 16-byte K chunks of one MMA
+__device__ __forceinline__ uint64_t smem_desc_interleaved(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (spin == 64) t0 = clock64();
-    if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();  // never hang the GPU
-  }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-// D = f32, A = B = bf16, K-major, N = 64, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr uint32_t kIdesc = idesc_bf16(128, 128);
 
-// two bytes (x = b0 | b1 << 8) -> packed bf16x2 of their integer values, exact.
+// four bytes -> two packed bf16x2 of their integer values, exact.
 // 0x4B000000 | v is the float 2^23 + v; subtracting 2^23 gives float(v) without the I2F pipe.
-__device__ __forceinline__ uint32_t bytes2_to_bf16x2(uint32_t x) {
+__device__ __forceinline__ uint2 bytes4_to_bf16x4(uint32_t x) {
   const float f0 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7440)) - 8388608.0f;
   const float f1 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7441)) - 8388608.0f;
-  __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
-  return *reinterpret_cast<uint32_t*>(&p);
+  const float f2 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7442)) - 8388608.0f;
+  const float f3 = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7443)) - 8388608.0f;
+  __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  return r;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams p) {
+__global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_raw + (base - raw);
-  // layout: A[3] | B | pool[2] | image | barriers | tmem slot
-  const uint32_t a_off = 0, b_off = kAStages * kABytes, pool_off = b_off + kBBytes, img_off = pool_off + 2 * kPoolBytes;
-  const int img_bytes = (kMaxImgRows + 1) * p.pitch;
-  const uint32_t bar_off = (img_off + img_bytes + 15u) & ~15u;
-  auto a_full = [&](int s) { return base + bar_off + 8u * s; };
-  auto a_empty = [&](int s) { return base + bar_off + 8u * (kAStages + s); };
-  auto t_full = [&](int s) { return base + bar_off + 8u * (2 * kAStages + s); };
-  auto t_empty = [&](int s) { return base + bar_off + 8u * (2 * kAStages + kSlots + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (2 * kAStages + 2 * kSlots));
+  // layout: E | B | pool[2] | image strip | bias | barriers | tmem slot
+  const uint32_t e_off = 0, b_off = kEBytes, pool_off = b_off + kBBytes, img_off = pool_off + 2 * kPoolBytes;
+  const int img_bytes = kERows * p.pitch;
+  const uint32_t bias_off = (img_off + img_bytes + 15u) & ~15u;
+  const uint32_t bar_off = bias_off + 64 * 4;
+  auto e_ready = [&](int i) { return base + bar_off + 8u * i; };                           // one per conv row of the strip
+  auto t_full = [&](int s) { return base + bar_off + 8u * (kMaxConvRows + s); };
+  auto t_empty = [&](int s) { return base + bar_off + 8u * (kMaxConvRows + kSlots + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kMaxConvRows + 2 * kSlots));
   unsigned char* img = gbase + img_off;
+  float* bias_sm = reinterpret_cast<float*>(gbase + bias_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int image = blockIdx.x / p.strips;
@@ -135,119 +102,105 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams
   const int p0 = strip * kPoolRowsPerStrip;
   const int p1 = min(p0 + kPoolRowsPerStrip, p.hp) - 1;  // last pooled row of the strip
   const int c_lo = max(0, 2 * p0 - 1), c_hi = min(p.hc - 1, 2 * p1 + 1);  // conv rows needed
-  const int i_lo = 2 * c_lo - 3;                                          // first input row (may be negative)
-  const int n_img_rows = 2 * (c_hi - c_lo) + 7;
+  const int y_base = 2 * c_lo - 3;                                         // input row of E row 0 (may be negative)
+  const int n_rows = c_hi - c_lo + 1;
 
-  // ---- zero the A ring (chunk 7 and rows >= m_count stay zero) and the image strip (padding)
+  // ---- zero E (padding rows / columns, columns >= wc) and the image strip (left / right padding)
   {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* a4 = reinterpret_cast<uint4*>(gbase + a_off);
-    for (int i = tid; i < kAStages * kABytes / 16; i += kThreads) a4[i] = z;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* e4 = reinterpret_cast<uint4*>(gbase + e_off);
+    for (int i = tid; i < kEBytes / 16; i += kThreads) e4[i] = z;
     uint4* i4 = reinterpret_cast<uint4*>(img);  // img_off is 16-byte aligned
     for (int i = tid; i < (img_bytes + 15) / 16; i += kThreads) i4[i] = z;
   }
+  if (tid < 64) bias_sm[tid] = __ldg(p.bias + tid);
   if (warp == 4) {
     if (lane == 0) {
-      for (int s = 0; s < kAStages; ++s) {
-        mbar_init(a_full(s), 4);
-        mbar_init(a_empty(s), 1);
-      }
+      for (int i = 0; i < kMaxConvRows; ++i) mbar_init(e_ready(i), 4);  // one arrival per builder warp
       for (int s = 0; s < kSlots; ++s) {
         mbar_init(t_full(s), 1);
         mbar_init(t_empty(s), 4);
       }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_init_fence();
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
-                 "r"((uint32_t)(kSlots * 64))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(smem_u32((const void*)tmem_slot), kSlots * 128);
   }
   __syncthreads();
-  // ---- stage the weights tile and the image strip
+  // ---- stage the weight tile and the u8 strip (pixel x of input row y lives at img[(y - y_base) * pitch + x + 3])
   {
     uint4* b4 = reinterpret_cast<uint4*>(gbase + b_off);
-    for (int i = tid; i < kBBytes / 16; i += kThreads) b4[i] = __ldg(p.w_sw + i);
+    for (int i = tid; i < kBBytes / 16; i += kThreads) b4[i] = __ldg(p.w_il + i);
     const uint8_t* src = p.x + (size_t)image * p.th * p.tw;
+    const int rows = 2 * (n_rows + 3);
     if ((p.tw & 3) == 0) {
       const int q_per_row = p.tw >> 2;
-      for (int e = tid; e < n_img_rows * q_per_row; e += kThreads) {
+      for (int e = tid; e < rows * q_per_row; e += kThreads) {
         const int rr = e / q_per_row, c4 = e - rr * q_per_row;
-        const int gr = i_lo + rr;
+        const int gr = y_base + rr;
         if (gr < 0 || gr >= p.th) continue;
         const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gr * p.tw) + c4);
-        unsigned char* d = img + rr * p.pitch + 3 + 4 * c4;  // pixel x lives at column x + 3
+        unsigned char* d = img + rr * p.pitch + 3 + 4 * c4;
         d[0] = (unsigned char)(v & 255u);
         d[1] = (unsigned char)((v >> 8) & 255u);
         d[2] = (unsigned char)((v >> 16) & 255u);
         d[3] = (unsigned char)(v >> 24);
       }
     } else {
-      for (int e = tid; e < n_img_rows * p.tw; e += kThreads) {
+      for (int e = tid; e < rows * p.tw; e += kThreads) {
         const int rr = e / p.tw, c = e - rr * p.tw;
-        const int gr = i_lo + rr;
+        const int gr = y_base + rr;
         if (gr < 0 || gr >= p.th) continue;
         img[rr * p.pitch + 3 + c] = __ldg(src + (size_t)gr * p.tw + c);
       }
     }
   }
-  // generic-proxy writes of B (and the zeroed A ring) must be visible to the tensor core (async proxy)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  // generic-proxy writes of B (and the zeroed E rows) must be visible to the tensor core (async proxy)
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_rows = c_hi - c_lo + 1;
 
   if (warp < 4) {
-    // ===== A builders =====
-    const int chunks = 7 * p.m_count;
-    for (int idx = 0; idx < n_rows; ++idx) {
-      const int s = idx % kAStages;
-      mbar_wait(a_empty(s), (((uint32_t)(idx / kAStages)) & 1u) ^ 1u);
-      unsigned char* a = gbase + a_off + s * kABytes;
-      const unsigned char* irow = img + (2 * idx) * p.pitch;  // input row 2*(c_lo+idx) - 3 == strip row 2*idx
-      int m = tid, r = 0;
-      while (m >= p.m_count) {
-        m -= p.m_count;
-        ++r;
+    // ===== E builders: step s writes E rows 2s and 2s+1; conv row idx needs steps 0 .. idx + 3 =====
+    const int sub = tid >> 6;        // which of the two rows of the step
+    const int pair = tid & 63;       // output columns 2*pair, 2*pair + 1
+    const bool col_ok = 2 * pair < p.wc;
+    for (int s = 0; s < n_rows + 3; ++s) {
+      const int yy = 2 * s + sub;
+      const int gy = y_base + yy;
+      if (col_ok && gy >= 0 && gy < p.th) {
+        // bytes [4*pair, 4*pair + 12) of the strip row = pixels 2j-3 .. 2j+8 for j = 2*pair
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(img + yy * p.pitch + 4 * pair);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        const uint2 a0 = bytes4_to_bf16x4(w0), a1 = bytes4_to_bf16x4(w1);
+        const uint2 b0 = bytes4_to_bf16x4(__funnelshift_r(w0, w1, 16)), b1 = bytes4_to_bf16x4(__funnelshift_r(w1, w2, 16));
+        uint4* dst = reinterpret_cast<uint4*>(gbase + e_off + yy * kERowBytes + (2 * pair) * 16);
+        dst[0] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+        dst[1] = make_uint4(b0.x, b0.y, b1.x, b1.y);
       }
-      for (int c = tid; c < chunks; c += kBuilders) {
-        const unsigned short* src = reinterpret_cast<const unsigned short*>(irow + r * p.pitch + 2 * m);
-        uint4 o;
-        o.x = bytes2_to_bf16x2(src[0]);
-        o.y = bytes2_to_bf16x2(src[1]);
-        o.z = bytes2_to_bf16x2(src[2]);
-        o.w = bytes2_to_bf16x2(src[3]);
-        *reinterpret_cast<uint4*>(a + m * 128 + ((r ^ (m & 7)) << 4)) = o;
-        m += kBuilders;
-        while (m >= p.m_count) {
-          m -= p.m_count;
-          ++r;
-        }
+      if (s >= 3) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(e_ready(s - 3));
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full(s));
     }
   } else if (warp == 4) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      const uint64_t b_hi = smem_desc_sw128(base + b_off);
-      const uint64_t b_lo = smem_desc_sw128(base + b_off + kBTile);
+      const uint32_t b_s = base + b_off;
       for (int idx = 0; idx < n_rows; ++idx) {
-        const int s = idx % kAStages, slot = idx % kSlots;
+        const int slot = idx % kSlots;
         mbar_wait(t_empty(slot), (((uint32_t)(idx / kSlots)) & 1u) ^ 1u);
-        mbar_wait(a_full(s), ((uint32_t)(idx / kAStages)) & 1u);
+        mbar_wait(e_ready(idx), 0);
         tc_fence_after();
-        const uint64_t a_desc = smem_desc_sw128(base + a_off + s * kABytes);
-        const uint32_t d = tmem_base + (uint32_t)(slot * 64);
+        const uint32_t a_s = base + e_off + (uint32_t)(2 * idx) * kERowBytes;  // E row of filter row 0
+        const uint32_t d = tmem_base + (uint32_t)(slot * 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma(d, a_desc + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), kIdesc, k != 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma(d, a_desc + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), kIdesc, 1u);
-        tc_commit(a_empty(s));
+        for (int k = 0; k < 4; ++k)  // K chunks 2k, 2k+1 = filter rows 2k, 2k+1
+          tc_mma(d, smem_desc_interleaved(a_s + 2u * k * kERowBytes, kERowBytes, 128),
+                 smem_desc_interleaved(b_s + 2u * k * 2048u, 2048, 128), kIdesc, k != 0 ? 1u : 0u);
         tc_commit(t_full(slot));
       }
     }
@@ -256,49 +209,53 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams
     const int q = warp & 3;          // TMEM lane quarter this warp may read
     const int wo = q * 32 + lane;    // conv output column == TMEM lane
     const int et = (warp - 5) * 32 + lane;  // 0..127 among the epilogue threads
-    float acc[64];
+    uint32_t acc[32];                // running vertical max, packed bf16x2 (post bias + ReLU, all >= 0)
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = -INFINITY;
+    for (int j = 0; j < 32; ++j) acc[j] = 0u;
     int emitted = 0;
     for (int idx = 0; idx < n_rows; ++idx) {
       const int i = c_lo + idx, slot = idx % kSlots;
       __syncwarp();  // tcgen05.ld below is warp-collective
       mbar_wait(t_full(slot), ((uint32_t)(idx / kSlots)) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
       const bool last_of_window = (i & 1) || (i == p.hc - 1);
       const int prow = i >> 1;
       const bool emit = last_of_window && prow >= p0 && prow <= p1;
-      {
-        uint32_t v[32];
-        tmem_ld32(taddr, v);
+      unsigned char* pool = gbase + pool_off + (emitted & 1) * kPoolBytes;
+      // 16 channels at a time: relu(hi + lo + bias) as packed bf16x2, vertical max, (emit:) row wo of the pool
+      // buffer in 16-byte chunks swizzled by (wo & 7), restart of the running max
+#pragma unroll
+      for (int qc = 0; qc < 4; ++qc) {
+        uint32_t hi[16], lo[16];
+        tmem_ld16(taddr + qc * 16, hi);
+        tmem_ld16(taddr + 64 + qc * 16, lo);
         tmem_ld_wait();
+        uint32_t cur[8], m[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], __uint_as_float(v[j]));
-        tmem_ld32(taddr + 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[32 + j] = fmaxf(acc[32 + j], __uint_as_float(v[j]));
-      }
-      if (emit) {
-        unsigned char* pool = gbase + pool_off + (emitted & 1) * kPoolBytes;
-        // + bias, ReLU, bf16; row wo of the pool buffer, 16-byte chunks swizzled by (wo & 7)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * j);
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * j + 1);
-          __nv_bfloat162 t0 = __floats2bfloat162_rn(fmaxf(acc[8 * j + 0] + b0.x, 0.f), fmaxf(acc[8 * j + 1] + b0.y, 0.f));
-          __nv_bfloat162 t1 = __floats2bfloat162_rn(fmaxf(acc[8 * j + 2] + b0.z, 0.f), fmaxf(acc[8 * j + 3] + b0.w, 0.f));
-          __nv_bfloat162 t2 = __floats2bfloat162_rn(fmaxf(acc[8 * j + 4] + b1.x, 0.f), fmaxf(acc[8 * j + 5] + b1.y, 0.f));
-          __nv_bfloat162 t3 = __floats2bfloat162_rn(fmaxf(acc[8 * j + 6] + b1.z, 0.f), fmaxf(acc[8 * j + 7] + b1.w, 0.f));
-          uint4 o;
-          o.x = *reinterpret_cast<uint32_t*>(&t0);
-          o.y = *reinterpret_cast<uint32_t*>(&t1);
-          o.z = *reinterpret_cast<uint32_t*>(&t2);
-          o.w = *reinterpret_cast<uint32_t*>(&t3);
-          *reinterpret_cast<uint4*>(pool + wo * 128 + ((j ^ (wo & 7)) << 4)) = o;
+        for (int j = 0; j < 16; j += 2) {
+          const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + qc * 16 + j);
+          const float v0 = fmaxf(__uint_as_float(hi[j]) + __uint_as_float(lo[j]) + b2.x, 0.f);
+          const float v1 = fmaxf(__uint_as_float(hi[j + 1]) + __uint_as_float(lo[j + 1]) + b2.y, 0.f);
+          __nv_bfloat162 t = __floats2bfloat162_rn(v0, v1);
+          cur[j >> 1] = *reinterpret_cast<uint32_t*>(&t);
+          __nv_bfloat162 mx = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&acc[qc * 8 + (j >> 1)]), t);
+          m[j >> 1] = *reinterpret_cast<uint32_t*>(&mx);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps
+        if (emit) {
+          *reinterpret_cast<uint4*>(pool + wo * 128 + (((2 * qc) ^ (wo & 7)) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<uint4*>(pool + wo * 128 + (((2 * qc + 1) ^ (wo & 7)) << 4)) = make_uint4(m[4], m[5], m[6], m[7]);
+        }
+        // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[qc * 8 + j] = last_of_window ? ((i & 1) ? cur[j] : 0u) : m[j];
+      }
+      // the accumulator slot is free as soon as it has been read
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty(slot));
+      if (emit) {
+        named_bar_sync(1, 128);  // the 4 epilogue warps
         // horizontal max over conv columns 2pw-1, 2pw, 2pw+1 and a coalesced store of the pooled row
         __nv_bfloat16* yrow = p.y + ((size_t)image * p.hp + prow) * p.wp * p.ldy;
         for (int o = et; o < p.wp * 8; o += 128) {
@@ -324,27 +281,6 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams
         }
         ++emitted;  // the other pool buffer is used next: one barrier per pooled row is enough
       }
-      if (last_of_window) {
-        // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it
-        // (re-read from TMEM rather than keeping 64 more registers live across the emit)
-        if (i & 1) {
-          uint32_t v[32];
-          tmem_ld32(taddr, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-          tmem_ld32(taddr + 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[32 + j] = __uint_as_float(v[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) acc[j] = -INFINITY;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty(slot));  // done with this accumulator slot
     }
   }
 
@@ -352,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_pool_kernel(const StemParams
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(kSlots * 64)) : "memory");
+    tmem_dealloc(tmem_base, kSlots * 128);
   }
 }
 
@@ -366,6 +302,9 @@ bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int poo
 }
 
 // w: folded [64][7][7] fp32 (already includes BatchNorm); the 1/255 of ToTensor is folded here.
+// Layout (interleaved K-major): K chunk kc = filter row r (8 of them, the last all zero), row n < 64 = bf16
+// hi part of output channel n, row 64 + n = its lo part, element e = filter column s (e = 7 zero):
+// byte offset kc * 2048 + row * 16 + e * 2.
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out) {
   std::vector<uint16_t> tile(kBBytes / 2, 0);
   for (int o = 0; o < 64; ++o)
@@ -377,22 +316,20 @@ int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out) {
         uint16_t bh, bl;
         memcpy(&bh, &hi, 2);
         memcpy(&bl, &lo, 2);
-        // row o, 16-byte chunk r at position (r ^ (o & 7)), element s
-        const size_t at = (size_t)o * 64 + ((r ^ (o & 7)) * 8) + s;
-        tile[at] = bh;
-        tile[kBTile / 2 + at] = bl;
+        tile[(size_t)r * 1024 + (size_t)o * 8 + s] = bh;
+        tile[(size_t)r * 1024 + (size_t)(64 + o) * 8 + s] = bl;
       }
   SPK_CUDA_OK(ctx, cudaMalloc(d_out, kBBytes));
   SPK_CUDA_OK(ctx, cudaMemcpy(*d_out, tile.data(), kBBytes, cudaMemcpyHostToDevice));
   return SPK_OK;
 }
 
-int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, const uint4* w_sw, const float* bias,
+int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, const uint4* w_il, const float* bias,
                      __nv_bfloat16* y, int hc, int wc, int hp, int wp, int ldy) {
   if (n <= 0) return SPK_OK;
   StemParams p;
   p.x = x;
-  p.w_sw = w_sw;
+  p.w_il = w_il;
   p.bias = bias;
   p.y = y;
   p.n = n;
@@ -404,10 +341,9 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
   p.wp = wp;
   p.ldy = ldy;
   p.strips = (hp + kPoolRowsPerStrip - 1) / kPoolRowsPerStrip;
-  p.m_count = (wc + 7) & ~7;
   p.pitch = (tw + kPitchPad + 15) & ~15;
-  const size_t smem = 1024 + kAStages * kABytes + kBBytes + 2 * kPoolBytes + (size_t)(kMaxImgRows + 1) * p.pitch + 16 +
-                      8 * (2 * kAStages + 2 * kSlots) + 16;
+  const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes + (size_t)kERows * p.pitch + 16 + 64 * 4 +
+                      8 * (kMaxConvRows + 2 * kSlots) + 16;
   SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   stem_pool_kernel<<<(unsigned)(n * p.strips), kThreads, smem, ctx->stream>>>(p);
   SPK_LAUNCH_CHECK(ctx);
