@@ -26,6 +26,7 @@
 // The 112x112x64 conv output (411 MB per 256 images in bf16) never exists in HBM.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "spk_internal.h"
@@ -36,7 +37,9 @@ namespace {
 using namespace tc;
 
 constexpr int kBuilders = 128;
-constexpr int kThreads = 288;           // 4 builder warps + 1 MMA warp + 4 epilogue warps
+constexpr int kEpiWarps = 8;            // two per TMEM lane quarter, 32 of the 64 channels each
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 160 + kEpiThreads;  // 4 builder warps + 1 MMA warp + 8 epilogue warps
 constexpr int kSlots = 2;               // TMEM accumulator ring: 2 x 128 columns (two CTAs share the SM's 512)
 constexpr int kPoolRowsPerStrip = 4;
 constexpr int kMaxConvRows = 2 * kPoolRowsPerStrip + 1;
@@ -47,7 +50,8 @@ constexpr int kEBytes = kERows * kERowBytes;
 constexpr int kBBytes = 8 * 128 * 16;     // weights: 8 K chunks x (64 hi + 64 lo rows) x 8 bf16
 constexpr int kPoolBytes = 128 * 128;
 constexpr int kMaxT = 256;
-constexpr int kPitchPad = 16;
+constexpr int kXOff = 16;       // column of pixel x = 0 in a strip row
+constexpr int kPitchPad = 32;   // kXOff + the builders' over-read past the last pixel
 
 struct StemParams {
   const uint8_t* x;      // [n, th, tw] u8
@@ -56,6 +60,7 @@ struct StemParams {
   __nv_bfloat16* y;      // [n, hp, wp, ldy]
   int n, th, tw, hc, wc, hp, wp, ldy;
   int strips, pitch;
+  int use_tma;           // strip staged by one TMA box (tw % 16 == 0, tw <= 224); else by the builder threads
 };
 
 // no-swizzle K-major descriptor: rows 16 B apart inside an 8-row core matrix, SBO between core matrices
@@ -79,7 +84,19 @@ __device__ __forceinline__ uint2 bytes4_to_bf16x4(uint32_t x) {
   return r;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams p) {
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const StemParams p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -92,7 +109,8 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
   auto e_ready = [&](int i) { return base + bar_off + 8u * i; };                           // one per conv row of the strip
   auto t_full = [&](int s) { return base + bar_off + 8u * (kMaxConvRows + s); };
   auto t_empty = [&](int s) { return base + bar_off + 8u * (kMaxConvRows + kSlots + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kMaxConvRows + 2 * kSlots));
+  const uint32_t load_bar = base + bar_off + 8u * (kMaxConvRows + 2 * kSlots);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kMaxConvRows + 2 * kSlots + 1));
   unsigned char* img = gbase + img_off;
   float* bias_sm = reinterpret_cast<float*>(gbase + bias_off);
 
@@ -105,58 +123,41 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
   const int y_base = 2 * c_lo - 3;                                         // input row of E row 0 (may be negative)
   const int n_rows = c_hi - c_lo + 1;
 
-  // ---- zero E (padding rows / columns, columns >= wc) and the image strip (left / right padding)
-  {
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* e4 = reinterpret_cast<uint4*>(gbase + e_off);
-    for (int i = tid; i < kEBytes / 16; i += kThreads) e4[i] = z;
-    uint4* i4 = reinterpret_cast<uint4*>(img);  // img_off is 16-byte aligned
-    for (int i = tid; i < (img_bytes + 15) / 16; i += kThreads) i4[i] = z;
-  }
   if (tid < 64) bias_sm[tid] = __ldg(p.bias + tid);
   if (warp == 4) {
     if (lane == 0) {
       for (int i = 0; i < kMaxConvRows; ++i) mbar_init(e_ready(i), 4);  // one arrival per builder warp
       for (int s = 0; s < kSlots; ++s) {
         mbar_init(t_full(s), 1);
-        mbar_init(t_empty(s), 4);
+        mbar_init(t_empty(s), kEpiWarps);
       }
+      mbar_init(load_bar, 1);
       mbar_init_fence();
+      // weight tile (16 KB, bulk copy) and, when the geometry allows, the u8 strip as ONE TMA box: pixel x of
+      // input row y lands at img[(y - y_base) * pitch + x + kXOff]; out-of-image rows / columns are zero-filled
+      mbar_expect_tx(load_bar, (uint32_t)kBBytes + (p.use_tma ? (uint32_t)(kERows * p.pitch) : 0u));
+      bulk_load(base + b_off, p.w_il, kBBytes, load_bar);
+      // (the box must start on a 16-byte boundary of the row: x = -16, not -3)
+      if (p.use_tma) tma_load_3d(base + img_off, &map_x, load_bar, -kXOff, y_base, image);
     }
     __syncwarp();
     tmem_alloc(smem_u32((const void*)tmem_slot), kSlots * 128);
   }
-  __syncthreads();
-  // ---- stage the weight tile and the u8 strip (pixel x of input row y lives at img[(y - y_base) * pitch + x + 3])
-  {
-    uint4* b4 = reinterpret_cast<uint4*>(gbase + b_off);
-    for (int i = tid; i < kBBytes / 16; i += kThreads) b4[i] = __ldg(p.w_il + i);
+  if (!p.use_tma) {
+    // manual staging (row pitch not a multiple of 16 bytes, or T > 240): zero the strip, then copy the rows
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* i4 = reinterpret_cast<uint4*>(img);  // img_off is 16-byte aligned
+    for (int i = tid; i < (img_bytes + 15) / 16; i += kThreads) i4[i] = z;
+    __syncthreads();
     const uint8_t* src = p.x + (size_t)image * p.th * p.tw;
     const int rows = 2 * (n_rows + 3);
-    if ((p.tw & 3) == 0) {
-      const int q_per_row = p.tw >> 2;
-      for (int e = tid; e < rows * q_per_row; e += kThreads) {
-        const int rr = e / q_per_row, c4 = e - rr * q_per_row;
-        const int gr = y_base + rr;
-        if (gr < 0 || gr >= p.th) continue;
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)gr * p.tw) + c4);
-        unsigned char* d = img + rr * p.pitch + 3 + 4 * c4;
-        d[0] = (unsigned char)(v & 255u);
-        d[1] = (unsigned char)((v >> 8) & 255u);
-        d[2] = (unsigned char)((v >> 16) & 255u);
-        d[3] = (unsigned char)(v >> 24);
-      }
-    } else {
-      for (int e = tid; e < rows * p.tw; e += kThreads) {
-        const int rr = e / p.tw, c = e - rr * p.tw;
-        const int gr = y_base + rr;
-        if (gr < 0 || gr >= p.th) continue;
-        img[rr * p.pitch + 3 + c] = __ldg(src + (size_t)gr * p.tw + c);
-      }
+    for (int e = tid; e < rows * p.tw; e += kThreads) {
+      const int rr = e / p.tw, c = e - rr * p.tw;
+      const int gr = y_base + rr;
+      if (gr < 0 || gr >= p.th) continue;
+      img[rr * p.pitch + kXOff + c] = __ldg(src + (size_t)gr * p.tw + c);
     }
   }
-  // generic-proxy writes of B (and the zeroed E rows) must be visible to the tensor core (async proxy)
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,13 +168,18 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
     const int sub = tid >> 6;        // which of the two rows of the step
     const int pair = tid & 63;       // output columns 2*pair, 2*pair + 1
     const bool col_ok = 2 * pair < p.wc;
+    mbar_wait(load_bar, 0);
     for (int s = 0; s < n_rows + 3; ++s) {
       const int yy = 2 * s + sub;
-      const int gy = y_base + yy;
-      if (col_ok && gy >= 0 && gy < p.th) {
-        // bytes [4*pair, 4*pair + 12) of the strip row = pixels 2j-3 .. 2j+8 for j = 2*pair
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(img + yy * p.pitch + 4 * pair);
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+      if (!col_ok) {  // columns past the conv width: finite zeros (their MMA rows are never read back)
+        uint4* dst = reinterpret_cast<uint4*>(gbase + e_off + yy * kERowBytes + (2 * pair) * 16);
+        dst[0] = make_uint4(0, 0, 0, 0);
+        dst[1] = make_uint4(0, 0, 0, 0);
+      } else {
+        // pixels 2j-3 .. 2j+8 for j = 2*pair = strip bytes [4*pair + 13, 4*pair + 25): four aligned words, shifted by one byte
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(img + yy * p.pitch + 4 * pair + (kXOff - 4));
+        const uint32_t v0 = w[0], v1 = w[1], v2 = w[2], v3 = w[3];
+        const uint32_t w0 = __funnelshift_r(v0, v1, 8), w1 = __funnelshift_r(v1, v2, 8), w2 = __funnelshift_r(v2, v3, 8);
         const uint2 a0 = bytes4_to_bf16x4(w0), a1 = bytes4_to_bf16x4(w1);
         const uint2 b0 = bytes4_to_bf16x4(__funnelshift_r(w0, w1, 16)), b1 = bytes4_to_bf16x4(__funnelshift_r(w1, w2, 16));
         uint4* dst = reinterpret_cast<uint4*>(gbase + e_off + yy * kERowBytes + (2 * pair) * 16);
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t b_s = base + b_off;
+      mbar_wait(load_bar, 0);
       for (int idx = 0; idx < n_rows; ++idx) {
         const int slot = idx % kSlots;
         mbar_wait(t_empty(slot), (((uint32_t)(idx / kSlots)) & 1u) ^ 1u);
@@ -205,20 +212,21 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
       }
     }
   } else {
-    // ===== epilogue =====
-    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    // ===== epilogue: warp w reads TMEM lanes [32 * (w % 4), +32) and channels [32 * half, +32) =====
+    const int q = warp & 3;
+    const int half = (warp - 5) >> 2;
     const int wo = q * 32 + lane;    // conv output column == TMEM lane
-    const int et = (warp - 5) * 32 + lane;  // 0..127 among the epilogue threads
-    uint32_t acc[32];                // running vertical max, packed bf16x2 (post bias + ReLU, all >= 0)
+    const int et = tid - 160;        // 0..255 among the epilogue threads
+    uint32_t acc[16];                // running vertical max, packed bf16x2 (post bias + ReLU, all >= 0)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0u;
+    for (int j = 0; j < 16; ++j) acc[j] = 0u;
     int emitted = 0;
     for (int idx = 0; idx < n_rows; ++idx) {
       const int i = c_lo + idx, slot = idx % kSlots;
       __syncwarp();  // tcgen05.ld below is warp-collective
       mbar_wait(t_full(slot), ((uint32_t)(idx / kSlots)) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + half * 32);
       const bool last_of_window = (i & 1) || (i == p.hc - 1);
       const int prow = i >> 1;
       const bool emit = last_of_window && prow >= p0 && prow <= p1;
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
       // 16 channels at a time: relu(hi + lo + bias) as packed bf16x2, vertical max, (emit:) row wo of the pool
       // buffer in 16-byte chunks swizzled by (wo & 7), restart of the running max
 #pragma unroll
-      for (int qc = 0; qc < 4; ++qc) {
+      for (int qc = 0; qc < 2; ++qc) {
         uint32_t hi[16], lo[16];
         tmem_ld16(taddr + qc * 16, hi);
         tmem_ld16(taddr + 64 + qc * 16, lo);
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
         uint32_t cur[8], m[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + qc * 16 + j);
+          const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + half * 32 + qc * 16 + j);
           const float v0 = fmaxf(__uint_as_float(hi[j]) + __uint_as_float(lo[j]) + b2.x, 0.f);
           const float v1 = fmaxf(__uint_as_float(hi[j + 1]) + __uint_as_float(lo[j + 1]) + b2.y, 0.f);
           __nv_bfloat162 t = __floats2bfloat162_rn(v0, v1);
@@ -243,8 +251,9 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
           m[j >> 1] = *reinterpret_cast<uint32_t*>(&mx);
         }
         if (emit) {
-          *reinterpret_cast<uint4*>(pool + wo * 128 + (((2 * qc) ^ (wo & 7)) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
-          *reinterpret_cast<uint4*>(pool + wo * 128 + (((2 * qc + 1) ^ (wo & 7)) << 4)) = make_uint4(m[4], m[5], m[6], m[7]);
+          const int c0 = 4 * half + 2 * qc;
+          *reinterpret_cast<uint4*>(pool + wo * 128 + ((c0 ^ (wo & 7)) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<uint4*>(pool + wo * 128 + (((c0 + 1) ^ (wo & 7)) << 4)) = make_uint4(m[4], m[5], m[6], m[7]);
         }
         // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it
 #pragma unroll
@@ -255,10 +264,10 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const StemParams
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty(slot));
       if (emit) {
-        named_bar_sync(1, 128);  // the 4 epilogue warps
+        named_bar_sync(1, kEpiThreads);  // the epilogue warps
         // horizontal max over conv columns 2pw-1, 2pw, 2pw+1 and a coalesced store of the pooled row
         __nv_bfloat16* yrow = p.y + ((size_t)image * p.hp + prow) * p.wp * p.ldy;
-        for (int o = et; o < p.wp * 8; o += 128) {
+        for (int o = et; o < p.wp * 8; o += kEpiThreads) {
           const int pw = o >> 3, j = o & 7;
           const int w1 = 2 * pw;
           uint4 m4 = *reinterpret_cast<const uint4*>(pool + w1 * 128 + ((j ^ (w1 & 7)) << 4));
@@ -341,11 +350,29 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
   p.wp = wp;
   p.ldy = ldy;
   p.strips = (hp + kPoolRowsPerStrip - 1) / kPoolRowsPerStrip;
-  p.pitch = (tw + kPitchPad + 15) & ~15;
-  const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes + (size_t)kERows * p.pitch + 16 + 64 * 4 +
-                      8 * (kMaxConvRows + 2 * kSlots) + 16;
+  static const bool no_tma = getenv("SPK_STEM_NO_TMA") != nullptr;  // A/B switch: stage the strip with the builder threads
+  p.use_tma = (!no_tma && tw % 16 == 0 && tw <= 224 && ((uintptr_t)x & 15) == 0 && encode_fn() != nullptr) ? 1 : 0;
+  p.pitch = p.use_tma ? 256 : ((tw + kPitchPad + 15) & ~15);
+  // the tensor map of the u8 batch {tw, th, n}, box {256, kERows, 1}: cached per (pointer, geometry)
+  static thread_local struct { const void* x; int n, th, tw; CUtensorMap map; } cache = {nullptr, 0, 0, 0, {}};
+  if (p.use_tma && (cache.x != x || cache.n < n || cache.th != th || cache.tw != tw)) {
+    cuuint64_t dims[3] = {(cuuint64_t)tw, (cuuint64_t)th, (cuuint64_t)n};
+    cuuint64_t strides[2] = {(cuuint64_t)tw, (cuuint64_t)tw * th};
+    cuuint32_t box[3] = {256u, (cuuint32_t)kERows, 1u};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn()(&cache.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(x), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SPK_ERR_CUDA, "stem: cuTensorMapEncodeTiled(u8 batch) failed: %d", (int)r);
+    cache.x = x;
+    cache.n = n;
+    cache.th = th;
+    cache.tw = tw;
+  }
+  const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes + (size_t)kERows * p.pitch + 32 + 64 * 4 +
+                      8 * (kMaxConvRows + 2 * kSlots + 1) + 16;
   SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  stem_pool_kernel<<<(unsigned)(n * p.strips), kThreads, smem, ctx->stream>>>(p);
+  stem_pool_kernel<<<(unsigned)(n * p.strips), kThreads, smem, ctx->stream>>>(cache.map, p);
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;
 }

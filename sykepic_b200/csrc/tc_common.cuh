@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 
 namespace spk {
 namespace tc {
@@ -37,7 +38,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (ok) return;
     // a pipeline bug must not hang the GPU: give up after ~2 s and raise a launch failure instead
     if (spin == 64) t0 = clock64();
-    if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("spk: mbarrier timeout: block %d thread %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 
