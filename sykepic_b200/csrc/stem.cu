@@ -7,10 +7,12 @@
 // one (w' = sum_c w[:, c]) and ToTensor's 1/255 is folded into the weights, so the A operand is the
 // exact integer pixel value in bf16.
 //
-// One CTA = one image x one strip of 4 pooled rows (9 conv rows), two CTAs per SM.
-// GEMM per conv output row: M = 128 (the row's <= 128 output columns), K = 64 (k = 8 r + s; s = 7 and
-// r = 7 carry zero weights), N = 128 (the 64 output channels twice: bf16 hi and bf16 lo part of the
-// weight, w = hi + lo to 2^-17, summed in the epilogue -- the stem keeps fp32-weight accuracy).
+// One CTA = one image x one strip of 4 pooled rows (9 conv rows), two CTAs per SM.  The kernel is bound by
+// instruction issue (ncu: 65 % issue-active), so the epilogue does one FMNMX per accumulator element.
+// GEMM per conv output row: M = 128 (the row's <= 128 output columns), N = 64, K = 2 x 64 (k = 8 r + s;
+// s = 7 and r = 7 carry zero weights; the operand is multiplied by the bf16 hi part and then by the bf16
+// lo part of the weight, w = hi + lo to 2^-17, into one accumulator -- the stem keeps fp32-weight
+// accuracy, which matters: bf16 stem weights alone raise the final probability error 1.5-3x).
 //
 // The A operand is never materialised per conv row.  For every INPUT row y the builder warps write
 //   E_y[j][0..8) = bf16(x[y][2j-3 .. 2j+5))        j = 0..127, 16 bytes each, 2 KB per input row,
@@ -20,9 +22,10 @@
 // rows, so the u8 -> bf16 expansion costs 2 input rows per conv row instead of 7.
 //   warps 0-3  stage the u8 strip, build E rows (2 per step), signal one mbarrier per conv row;
 //   warp 4     allocates TMEM, issues tcgen05.mma (one thread), commits to mbarriers;
-//   warps 5-8  epilogue: tcgen05.ld hi + lo, + bias, ReLU, bf16, running vertical max of the 3 conv
-//              rows of a pooled row as packed bf16x2 (max commutes with the monotone bias / ReLU /
-//              rounding), horizontal max through shared memory, coalesced 16-byte stores.
+//   warps 5-12 epilogue (two per TMEM lane quarter, 32 channels each): tcgen05.ld, running vertical max
+//              of the 3 conv rows of a pooled row on the raw fp32 sums (max commutes with the monotone
+//              bias / ReLU / rounding, applied once per pooled row), horizontal max through shared
+//              memory, coalesced 16-byte stores.
 // The 112x112x64 conv output (411 MB per 256 images in bf16) never exists in HBM.
 #include <cuda.h>
 
@@ -40,14 +43,15 @@ constexpr int kBuilders = 128;
 constexpr int kEpiWarps = 8;            // two per TMEM lane quarter, 32 of the 64 channels each
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 160 + kEpiThreads;  // 4 builder warps + 1 MMA warp + 8 epilogue warps
-constexpr int kSlots = 2;               // TMEM accumulator ring: 2 x 128 columns (two CTAs share the SM's 512)
+constexpr int kSlots = 4;               // TMEM accumulator ring: 4 x 64 columns (two CTAs share the SM's 512)
 constexpr int kPoolRowsPerStrip = 4;
 constexpr int kMaxConvRows = 2 * kPoolRowsPerStrip + 1;
 constexpr int kSteps = kMaxConvRows + 3;  // builder steps (2 input rows each)
 constexpr int kERows = 2 * kSteps;        // E rows of a strip (the last one only meets zero weights)
 constexpr int kERowBytes = 128 * 16;      // one E row: 128 output columns x 8 bf16
 constexpr int kEBytes = kERows * kERowBytes;
-constexpr int kBBytes = 8 * 128 * 16;     // weights: 8 K chunks x (64 hi + 64 lo rows) x 8 bf16
+constexpr int kBTile = 8 * 64 * 16;       // one weight tile: 8 K chunks x 64 rows x 8 bf16
+constexpr int kBBytes = 2 * kBTile;       // bf16 hi tile + bf16 lo tile
 constexpr int kPoolBytes = 128 * 128;
 constexpr int kMaxT = 256;
 constexpr int kXOff = 16;       // column of pixel x = 0 in a strip row
@@ -68,7 +72,7 @@ struct StemParams {
 __device__ __forceinline__ uint64_t smem_desc_interleaved(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
-constexpr uint32_t kIdesc = idesc_bf16(128, 128);
+constexpr uint32_t kIdesc = idesc_bf16(128, 64);
 
 // four bytes -> two packed bf16x2 of their integer values, exact.
 // 0x4B000000 | v is the float 2^23 + v; subtracting 2^23 gives float(v) without the I2F pipe.
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
       if (p.use_tma) tma_load_3d(base + img_off, &map_x, load_bar, -kXOff, y_base, image);
     }
     __syncwarp();
-    tmem_alloc(smem_u32((const void*)tmem_slot), kSlots * 128);
+    tmem_alloc(smem_u32((const void*)tmem_slot), kSlots * 64);
   }
   if (!p.use_tma) {
     // manual staging (row pitch not a multiple of 16 bytes, or T > 240): zero the strip, then copy the rows
@@ -203,11 +207,14 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
         mbar_wait(e_ready(idx), 0);
         tc_fence_after();
         const uint32_t a_s = base + e_off + (uint32_t)(2 * idx) * kERowBytes;  // E row of filter row 0
-        const uint32_t d = tmem_base + (uint32_t)(slot * 128);
+        const uint32_t d = tmem_base + (uint32_t)(slot * 64);
+        // K = 128: the eight 16-byte K chunks (filter rows) against the hi weights, then again against the lo weights
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // K chunks 2k, 2k+1 = filter rows 2k, 2k+1
-          tc_mma(d, smem_desc_interleaved(a_s + 2u * k * kERowBytes, kERowBytes, 128),
-                 smem_desc_interleaved(b_s + 2u * k * 2048u, 2048, 128), kIdesc, k != 0 ? 1u : 0u);
+        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma(d, smem_desc_interleaved(a_s + 2u * k * kERowBytes, kERowBytes, 128),
+                   smem_desc_interleaved(b_s + (uint32_t)pass * kBTile + 2u * k * 1024u, 1024, 128), kIdesc, (pass | k) != 0 ? 1u : 0u);
         tc_commit(t_full(slot));
       }
     }
@@ -217,47 +224,46 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
     const int half = (warp - 5) >> 2;
     const int wo = q * 32 + lane;    // conv output column == TMEM lane
     const int et = tid - 160;        // 0..255 among the epilogue threads
-    uint32_t acc[16];                // running vertical max, packed bf16x2 (post bias + ReLU, all >= 0)
+    float acc[32];                   // running vertical max of the raw conv sums (bias / ReLU / rounding are monotone:
+                                     // they are applied once per pooled row, after the max)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0u;
+    for (int j = 0; j < 32; ++j) acc[j] = -INFINITY;
     int emitted = 0;
     for (int idx = 0; idx < n_rows; ++idx) {
       const int i = c_lo + idx, slot = idx % kSlots;
       __syncwarp();  // tcgen05.ld below is warp-collective
       mbar_wait(t_full(slot), ((uint32_t)(idx / kSlots)) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + half * 32);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64 + half * 32);
       const bool last_of_window = (i & 1) || (i == p.hc - 1);
       const int prow = i >> 1;
       const bool emit = last_of_window && prow >= p0 && prow <= p1;
       unsigned char* pool = gbase + pool_off + (emitted & 1) * kPoolBytes;
-      // 16 channels at a time: relu(hi + lo + bias) as packed bf16x2, vertical max, (emit:) row wo of the pool
-      // buffer in 16-byte chunks swizzled by (wo & 7), restart of the running max
 #pragma unroll
       for (int qc = 0; qc < 2; ++qc) {
-        uint32_t hi[16], lo[16];
-        tmem_ld16(taddr + qc * 16, hi);
-        tmem_ld16(taddr + 64 + qc * 16, lo);
+        uint32_t v[16];
+        tmem_ld16(taddr + qc * 16, v);
         tmem_ld_wait();
-        uint32_t cur[8], m[8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + half * 32 + qc * 16 + j);
-          const float v0 = fmaxf(__uint_as_float(hi[j]) + __uint_as_float(lo[j]) + b2.x, 0.f);
-          const float v1 = fmaxf(__uint_as_float(hi[j + 1]) + __uint_as_float(lo[j + 1]) + b2.y, 0.f);
-          __nv_bfloat162 t = __floats2bfloat162_rn(v0, v1);
-          cur[j >> 1] = *reinterpret_cast<uint32_t*>(&t);
-          __nv_bfloat162 mx = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&acc[qc * 8 + (j >> 1)]), t);
-          m[j >> 1] = *reinterpret_cast<uint32_t*>(&mx);
-        }
-        if (emit) {
-          const int c0 = 4 * half + 2 * qc;
-          *reinterpret_cast<uint4*>(pool + wo * 128 + ((c0 ^ (wo & 7)) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
-          *reinterpret_cast<uint4*>(pool + wo * 128 + (((c0 + 1) ^ (wo & 7)) << 4)) = make_uint4(m[4], m[5], m[6], m[7]);
-        }
-        // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it
+        for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = fmaxf(acc[qc * 16 + j], __uint_as_float(v[j]));
+        if (last_of_window) {
+          if (emit) {
+            // + bias, ReLU, bf16; row wo of the pool buffer in 16-byte chunks swizzled by (wo & 7)
+            uint32_t o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[qc * 8 + j] = last_of_window ? ((i & 1) ? cur[j] : 0u) : m[j];
+            for (int j = 0; j < 16; j += 2) {
+              const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + half * 32 + qc * 16 + j);
+              __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(acc[qc * 16 + j] + b2.x, 0.f), fmaxf(acc[qc * 16 + j + 1] + b2.y, 0.f));
+              o[j >> 1] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            const int c0 = 4 * half + 2 * qc;
+            *reinterpret_cast<uint4*>(pool + wo * 128 + ((c0 ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(pool + wo * 128 + (((c0 + 1) ^ (wo & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = (i & 1) ? __uint_as_float(v[j]) : -INFINITY;
+        }
       }
       // the accumulator slot is free as soon as it has been read
       tc_fence_before();
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kSlots * 128);
+    tmem_dealloc(tmem_base, kSlots * 64);
   }
 }
 
@@ -311,9 +317,9 @@ bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int poo
 }
 
 // w: folded [64][7][7] fp32 (already includes BatchNorm); the 1/255 of ToTensor is folded here.
-// Layout (interleaved K-major): K chunk kc = filter row r (8 of them, the last all zero), row n < 64 = bf16
-// hi part of output channel n, row 64 + n = its lo part, element e = filter column s (e = 7 zero):
-// byte offset kc * 2048 + row * 16 + e * 2.
+// Two tiles (bf16 hi part, bf16 lo part of the weight) in the interleaved K-major layout: K chunk kc = filter
+// row r (8 of them, the last all zero), row n = output channel, element e = filter column s (e = 7 zero):
+// byte offset kc * 1024 + n * 16 + e * 2.
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out) {
   std::vector<uint16_t> tile(kBBytes / 2, 0);
   for (int o = 0; o < 64; ++o)
@@ -325,8 +331,8 @@ int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out) {
         uint16_t bh, bl;
         memcpy(&bh, &hi, 2);
         memcpy(&bl, &lo, 2);
-        tile[(size_t)r * 1024 + (size_t)o * 8 + s] = bh;
-        tile[(size_t)r * 1024 + (size_t)(64 + o) * 8 + s] = bl;
+        tile[(size_t)r * 512 + (size_t)o * 8 + s] = bh;
+        tile[(size_t)kBTile / 2 + (size_t)r * 512 + (size_t)o * 8 + s] = bl;
       }
   SPK_CUDA_OK(ctx, cudaMalloc(d_out, kBBytes));
   SPK_CUDA_OK(ctx, cudaMemcpy(*d_out, tile.data(), kBBytes, cudaMemcpyHostToDevice));

@@ -24,23 +24,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Wait for the phase with the given parity.  mbarrier.try_wait suspends the thread in hardware until the phase
+// completes or the time hint (ns) runs out, so the loop around it executes a handful of instructions per
+// millisecond instead of spinning on the issue port (ncu on the stem kernel: 19 % of all issued instructions
+// were spin-wait iterations before the hint was added).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   long long t0 = 0;
-  for (uint32_t spin = 0;; ++spin) {
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(1000000u)
         : "memory");
     if (ok) return;
     // a pipeline bug must not hang the GPU: give up after ~2 s and raise a launch failure instead
-    if (spin == 64) t0 = clock64();
-    if (spin > 64 && (spin & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
-      printf("spk: mbarrier timeout: block %d thread %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
+    if (it >= 8) {
+      if (t0 == 0) {
+        t0 = clock64();
+      } else if (clock64() - t0 > 4000000000LL) {
+        printf("spk: mbarrier timeout: block %d thread %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 }
