@@ -50,6 +50,7 @@ constexpr int kSteps = kMaxConvRows + 3;  // builder steps (2 input rows each)
 constexpr int kERows = 2 * kSteps;        // E rows of a strip (the last one only meets zero weights)
 constexpr int kERowBytes = 128 * 16;      // one E row: 128 output columns x 8 bf16
 constexpr int kEBytes = kERows * kERowBytes;
+constexpr int kEGroups = kERows / 4;      // the builders signal every 4 E rows
 constexpr int kBTile = 8 * 64 * 16;       // one weight tile: 8 K chunks x 64 rows x 8 bf16
 constexpr int kBBytes = 2 * kBTile;       // bf16 hi tile + bf16 lo tile
 constexpr int kPoolBytes = 128 * 128;
@@ -64,6 +65,8 @@ struct StemParams {
   __nv_bfloat16* y;      // [n, hp, wp, ldy]
   int n, th, tw, hc, wc, hp, wp, ldy;
   int strips, pitch;
+  int groups, rb_pitch;  // 16-pixel groups per strip row that are converted to bf16; byte pitch of the bf16 row buffer
+  long long* trace;      // debug: clock64 timestamps of a few CTAs (SPK_STEM_TRACE=1), else nullptr
   int use_tma;           // strip staged by one TMA box (tw % 16 == 0, tw <= 224); else by the builder threads
 };
 
@@ -100,6 +103,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+#define STEM_TRACE(slot)                                                                         \
+  do {                                                                                           \
+    if (p.trace && (blockIdx.x % 1000) == 500) p.trace[(blockIdx.x / 1000) * 64 + (slot)] = clock64(); \
+  } while (0)
+
 __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const StemParams p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -110,11 +118,12 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
   const int img_bytes = kERows * p.pitch;
   const uint32_t bias_off = (img_off + img_bytes + 15u) & ~15u;
   const uint32_t bar_off = bias_off + 64 * 4;
-  auto e_ready = [&](int i) { return base + bar_off + 8u * i; };                           // one per conv row of the strip
-  auto t_full = [&](int s) { return base + bar_off + 8u * (kMaxConvRows + s); };
-  auto t_empty = [&](int s) { return base + bar_off + 8u * (kMaxConvRows + kSlots + s); };
-  const uint32_t load_bar = base + bar_off + 8u * (kMaxConvRows + 2 * kSlots);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kMaxConvRows + 2 * kSlots + 1));
+  auto e_ready = [&](int g) { return base + bar_off + 8u * g; };  // E rows [4g, 4g + 4) are built
+  auto t_full = [&](int s) { return base + bar_off + 8u * (kEGroups + s); };
+  auto t_empty = [&](int s) { return base + bar_off + 8u * (kEGroups + kSlots + s); };
+  const uint32_t load_bar = base + bar_off + 8u * (kEGroups + 2 * kSlots);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kEGroups + 1 + 2 * kSlots));
+  unsigned char* rowbuf = gbase + pool_off;  // bf16 copy of the strip; aliases the pool buffers, which are idle until the first MMA is done
   unsigned char* img = gbase + img_off;
   float* bias_sm = reinterpret_cast<float*>(gbase + bias_off);
 
@@ -127,10 +136,18 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
   const int y_base = 2 * c_lo - 3;                                         // input row of E row 0 (may be negative)
   const int n_rows = c_hi - c_lo + 1;
 
+  if (tid == 0) {
+    STEM_TRACE(0);
+    if (p.trace && (blockIdx.x % 1000) == 500) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[(blockIdx.x / 1000) * 64 + 6] = smid;
+    }
+  }
   if (tid < 64) bias_sm[tid] = __ldg(p.bias + tid);
   if (warp == 4) {
     if (lane == 0) {
-      for (int i = 0; i < kMaxConvRows; ++i) mbar_init(e_ready(i), 4);  // one arrival per builder warp
+      for (int g = 0; g < kEGroups; ++g) mbar_init(e_ready(g), 4);  // one arrival per builder warp
       for (int s = 0; s < kSlots; ++s) {
         mbar_init(t_full(s), 1);
         mbar_init(t_empty(s), kEpiWarps);
@@ -166,46 +183,58 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) STEM_TRACE(1);
+
+  // ---- u8 -> bf16, ONCE per pixel (all threads): element e of a row-buffer row is pixel x = e - 3, so that the
+  // operand chunk of output column j (pixels 2j-3 .. 2j+4) starts at element 2j = byte 4j
+  mbar_wait(load_bar, 0);
+  if (tid == 0) STEM_TRACE(2);
+  for (int task = tid; task < kERows * p.groups; task += kThreads) {
+    const int rr = task / p.groups, g = task - rr * p.groups;
+    // pixels 16g-3 .. 16g+12 = strip bytes [16g + 13, 16g + 29): two aligned 16-byte loads, shifted by one byte
+    const uint4* src = reinterpret_cast<const uint4*>(img + rr * p.pitch + 16 * g);
+    const uint4 lo4 = src[0], hi4 = src[1];
+    const uint32_t u0 = __funnelshift_r(lo4.w, hi4.x, 8), u1 = __funnelshift_r(hi4.x, hi4.y, 8);
+    const uint32_t u2 = __funnelshift_r(hi4.y, hi4.z, 8), u3 = __funnelshift_r(hi4.z, hi4.w, 8);
+    const uint2 c0 = bytes4_to_bf16x4(u0), c1 = bytes4_to_bf16x4(u1), c2 = bytes4_to_bf16x4(u2), c3 = bytes4_to_bf16x4(u3);
+    uint4* dst = reinterpret_cast<uint4*>(rowbuf + rr * p.rb_pitch + 32 * g);
+    dst[0] = make_uint4(c0.x, c0.y, c1.x, c1.y);
+    dst[1] = make_uint4(c2.x, c2.y, c3.x, c3.y);
+  }
+  __syncthreads();
+  if (tid == 0) STEM_TRACE(3);
 
   if (warp < 4) {
-    // ===== E builders: step s writes E rows 2s and 2s+1; conv row idx needs steps 0 .. idx + 3 =====
-    const int sub = tid >> 6;        // which of the two rows of the step
-    const int pair = tid & 63;       // output columns 2*pair, 2*pair + 1
-    const bool col_ok = 2 * pair < p.wc;
-    mbar_wait(load_bar, 0);
-    for (int s = 0; s < n_rows + 3; ++s) {
-      const int yy = 2 * s + sub;
-      if (!col_ok) {  // columns past the conv width: finite zeros (their MMA rows are never read back)
-        uint4* dst = reinterpret_cast<uint4*>(gbase + e_off + yy * kERowBytes + (2 * pair) * 16);
-        dst[0] = make_uint4(0, 0, 0, 0);
-        dst[1] = make_uint4(0, 0, 0, 0);
-      } else {
-        // pixels 2j-3 .. 2j+8 for j = 2*pair = strip bytes [4*pair + 13, 4*pair + 25): four aligned words, shifted by one byte
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(img + yy * p.pitch + 4 * pair + (kXOff - 4));
-        const uint32_t v0 = w[0], v1 = w[1], v2 = w[2], v3 = w[3];
-        const uint32_t w0 = __funnelshift_r(v0, v1, 8), w1 = __funnelshift_r(v1, v2, 8), w2 = __funnelshift_r(v2, v3, 8);
-        const uint2 a0 = bytes4_to_bf16x4(w0), a1 = bytes4_to_bf16x4(w1);
-        const uint2 b0 = bytes4_to_bf16x4(__funnelshift_r(w0, w1, 16)), b1 = bytes4_to_bf16x4(__funnelshift_r(w1, w2, 16));
-        uint4* dst = reinterpret_cast<uint4*>(gbase + e_off + yy * kERowBytes + (2 * pair) * 16);
-        dst[0] = make_uint4(a0.x, a0.y, a1.x, a1.y);
-        dst[1] = make_uint4(b0.x, b0.y, b1.x, b1.y);
+    // ===== E builders: pure copies.  E[j] = bytes [4j, 4j + 16) of the row buffer; consecutive lanes take
+    // consecutive columns, so both the 4-byte loads and the 16-byte stores of a warp are contiguous
+    // (a thread-owns-4-columns mapping was measured: 16-way bank conflicts on the stores, 3200 cycles) =====
+    for (int yy = warp; yy < kERows; yy += 4) {
+      const unsigned char* r = rowbuf + yy * p.rb_pitch;
+      unsigned char* e = gbase + e_off + yy * kERowBytes;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = lane + 32 * c;
+        if (j < p.wc) {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(r + 4 * j);
+          *reinterpret_cast<uint4*>(e + j * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
-      if (s >= 3) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(e_ready(s - 3));
-      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(e_ready(yy >> 2));
     }
+    if (tid == 0) STEM_TRACE(4);
   } else if (warp == 4) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t b_s = base + b_off;
-      mbar_wait(load_bar, 0);
+      int groups_seen = 0;
       for (int idx = 0; idx < n_rows; ++idx) {
         const int slot = idx % kSlots;
+        for (; groups_seen <= (2 * idx + 7) >> 2; ++groups_seen) mbar_wait(e_ready(groups_seen), 0);  // E rows 2idx .. 2idx+7
         mbar_wait(t_empty(slot), (((uint32_t)(idx / kSlots)) & 1u) ^ 1u);
-        mbar_wait(e_ready(idx), 0);
         tc_fence_after();
+        STEM_TRACE(8 + idx);
         const uint32_t a_s = base + e_off + (uint32_t)(2 * idx) * kERowBytes;  // E row of filter row 0
         const uint32_t d = tmem_base + (uint32_t)(slot * 64);
         // K = 128: the eight 16-byte K chunks (filter rows) against the hi weights, then again against the lo weights
@@ -234,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
       __syncwarp();  // tcgen05.ld below is warp-collective
       mbar_wait(t_full(slot), ((uint32_t)(idx / kSlots)) & 1u);
       tc_fence_after();
+      if (tid == 160) STEM_TRACE(24 + idx);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64 + half * 32);
       const bool last_of_window = (i & 1) || (i == p.hc - 1);
       const int prow = i >> 1;
@@ -269,8 +299,11 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty(slot));
+      if (tid == 160 && idx == 2) STEM_TRACE(56);
+      if (tid == 415 && idx == 2) STEM_TRACE(59);
       if (emit) {
         named_bar_sync(1, kEpiThreads);  // the epilogue warps
+        if (tid == 160 && idx == 2) STEM_TRACE(57);
         // horizontal max over conv columns 2pw-1, 2pw, 2pw+1 and a coalesced store of the pooled row
         __nv_bfloat16* yrow = p.y + ((size_t)image * p.hp + prow) * p.wp * p.ldy;
         for (int o = et; o < p.wp * 8; o += kEpiThreads) {
@@ -296,11 +329,13 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
         }
         ++emitted;  // the other pool buffer is used next: one barrier per pooled row is enough
       }
+      if (tid == 160) STEM_TRACE(40 + idx);
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) STEM_TRACE(5);
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kSlots * 64);
@@ -358,7 +393,9 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
   p.strips = (hp + kPoolRowsPerStrip - 1) / kPoolRowsPerStrip;
   static const bool no_tma = getenv("SPK_STEM_NO_TMA") != nullptr;  // A/B switch: stage the strip with the builder threads
   p.use_tma = (!no_tma && tw % 16 == 0 && tw <= 224 && ((uintptr_t)x & 15) == 0 && encode_fn() != nullptr) ? 1 : 0;
-  p.pitch = p.use_tma ? 256 : ((tw + kPitchPad + 15) & ~15);
+  p.groups = (tw + 16 + 15) / 16;                       // row-buffer elements [0, 16 * groups) cover pixels up to tw + 12
+  p.rb_pitch = 32 * p.groups + 32;                      // + slack for the dead columns' over-read
+  p.pitch = p.use_tma ? 256 : (16 * p.groups + 32);     // strip bytes read: up to 16 * groups + 15
   // the tensor map of the u8 batch {tw, th, n}, box {256, kERows, 1}: cached per (pointer, geometry)
   static thread_local struct { const void* x; int n, th, tw; CUtensorMap map; } cache = {nullptr, 0, 0, 0, {}};
   if (p.use_tma && (cache.x != x || cache.n < n || cache.th != th || cache.tw != tw)) {
@@ -376,10 +413,37 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     cache.tw = tw;
   }
   const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes + (size_t)kERows * p.pitch + 32 + 64 * 4 +
-                      8 * (kMaxConvRows + 2 * kSlots + 1) + 16;
+                      8 * (kEGroups + 1 + 2 * kSlots) + 16;
   SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool want_trace = getenv("SPK_STEM_TRACE") != nullptr;
+  static long long* d_trace = nullptr;
+  static int trace_left = 3;
+  p.trace = nullptr;
+  if (want_trace && trace_left > 0) {
+    if (!d_trace) cudaMalloc(&d_trace, 16 * 64 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 16 * 64 * sizeof(long long), ctx->stream);
+    p.trace = d_trace;
+  }
   stem_pool_kernel<<<(unsigned)(n * p.strips), kThreads, smem, ctx->stream>>>(cache.map, p);
   SPK_LAUNCH_CHECK(ctx);
+  if (p.trace) {
+    --trace_left;
+    std::vector<long long> h(16 * 64);
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    for (int c = 0; c < 4; ++c) {
+      const long long* t = &h[(size_t)c * 64];
+      if (!t[0]) continue;
+      fprintf(stderr, "stem trace cta %d sm %lld: sync1 %lld load %lld convert %lld e_done %lld end %lld\n  mma:", c * 1000 + 500, t[6], t[1] - t[0],
+              t[2] - t[0], t[3] - t[0], t[4] - t[0], t[5] - t[0]);
+      for (int i = 0; i < 9; ++i) fprintf(stderr, " %lld", t[8 + i] ? t[8 + i] - t[0] : -1);
+      fprintf(stderr, "\n  epi wake:");
+      for (int i = 0; i < 9; ++i) fprintf(stderr, " %lld", t[24 + i] ? t[24 + i] - t[0] : -1);
+      fprintf(stderr, "\n  epi done:");
+      for (int i = 0; i < 9; ++i) fprintf(stderr, " %lld", t[40 + i] ? t[40 + i] - t[0] : -1);
+      fprintf(stderr, "\n  row2: before barrier %lld (last warp %lld) after barrier %lld\n", t[56] - t[0], t[59] - t[0], t[57] - t[0]);
+    }
+  }
   return SPK_OK;
 }
 
