@@ -22,6 +22,7 @@
 // Persistent CTAs (one per SM), warp-specialised: warp 0 = A/B TMA producer, warp 1 = TMEM allocation +
 // MMA issuer, warp 2 = residual producer, warps 3-6 = epilogue.  Accumulators are double-buffered in TMEM.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "spk_internal.h"
@@ -46,6 +47,7 @@ struct alignas(64) HaloParams {
   int io_bytes;     // w * hb * 128: box bytes of an output / residual slab
   int io_slot;      // io_bytes rounded up to 1024
   int na, nb;       // ring depths
+  long long* trace; // debug (SPK_HALO_TRACE=1): clock64 stamps of CTA 5's MMA issuer, else nullptr
 };
 
 template <int BN, int MT, bool BRES>
@@ -163,11 +165,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       }
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
+      int tr = 0;
+      const bool tracing = p.trace != nullptr && blockIdx.x == 5;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int m0 = (u / p.tiles_n) * MT;
         const int nvalid = min(MT, p.m_tiles - m0);
+        if (tracing && tr < 250) p.trace[tr++] = clock64();
         mbar_wait(t_empty(acc), accph ^ 1u);  // the epilogue has drained this accumulator buffer
         tc_fence_after();
+        if (tracing && tr < 250) p.trace[tr++] = clock64();
         for (int ch = 0; ch < p.kchunks; ++ch) {
           int slot[MT];
 #pragma unroll
@@ -182,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
             }
           }
           tc_fence_after();
+          if (tracing && tr < 250) p.trace[tr++] = clock64();
           for (int tap = 0; tap < 9; ++tap) {
             const int r = tap / 3, s = tap - 3 * r;
             uint32_t b_addr;
@@ -190,6 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
             } else {
               mbar_wait(b_full(bs), bph);
               tc_fence_after();
+              if (tracing && tr < 250) p.trace[tr++] = clock64();
               b_addr = b_s + (uint32_t)bs * kBTile;
             }
             const uint64_t b_desc = smem_desc_sw128(b_addr);
@@ -409,8 +417,27 @@ static int halo_launch_t(spk_ctx* ctx, HaloConvPlan* p) {
     attr_done[ctx->device & 63] = true;
   }
   const int grid = std::min(p->prm.units, ctx->sm_count);
+  static const bool want_trace = getenv("SPK_HALO_TRACE") != nullptr;
+  static long long* d_trace = nullptr;
+  static int trace_left = 6;
+  p->prm.trace = nullptr;
+  if (want_trace && trace_left > 0) {
+    if (!d_trace) cudaMalloc(&d_trace, 256 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 256 * sizeof(long long), ctx->stream);
+    p->prm.trace = d_trace;
+  }
   conv3x3_halo_kernel<BN, MT, BRES><<<grid, kThreads, p->smem, ctx->stream>>>(p->prm);
   SPK_LAUNCH_CHECK(ctx);
+  if (p->prm.trace) {
+    --trace_left;
+    long long h[256];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "halo trace BN=%d MT=%d BRES=%d cin=%d w=%d units=%d na=%d nb=%d (cycles since the first stamp; per unit: start, t_empty, then per chunk: a_full%s):\n ",
+            BN, MT, (int)BRES, p->prm.cin, p->prm.w, p->prm.units, p->prm.na, p->prm.nb, BRES ? "" : ", b_full x9");
+    for (int i = 0; i < 250 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    fprintf(stderr, "\n");
+  }
   return SPK_OK;
 }
 

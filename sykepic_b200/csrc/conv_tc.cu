@@ -41,9 +41,13 @@ constexpr int kABytes = kBM * kBK * 2;
 struct alignas(64) TcParams {
   CUtensorMap map_a[4];
   CUtensorMap map_b;
+  CUtensorMap map_b2;  // fused 1x1 stride-2 downsample: weights [Cout][cin_pad] applied to the centre tap's A tiles
   const float* bias;
   const __nv_bfloat16* res;
   __nv_bfloat16* y;
+  const float* bias2;
+  __nv_bfloat16* y2;
+  int ldy2, ds_tap;
   int n, ho, wo, cout, ldy, ldres, relu;
   int wb, hb, nb;
   int tiles_w, tiles_h, tiles_img, tiles_n;
@@ -133,21 +137,22 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
          ((uint64_t)2 << 61);
 }
 
-template <int BN>
+template <int BN, bool DS = false>
 struct Cfg {
   static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;  // double-buffered accumulator (power of two)
+  static constexpr int kStageBytes = kABytes + kBBytes * (DS ? 2 : 1);
+  static constexpr int kStages = DS ? 4 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int kAccCols = DS ? 2 * BN : BN;            // main accumulator (+ the downsample's beside it)
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;  // double-buffered (power of two)
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10),
   // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 };
 
-template <int BN>
+template <int BN, bool DS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, DS>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&p.map_b);
     tma_prefetch_desc(&p.map_a[0]);
+    if (DS) tma_prefetch_desc(&p.map_b2);
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
@@ -206,9 +212,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int c0 = (kb - tap * p.kchunks) * kBK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::kStageBytes;
-          mbar_expect_tx(full_bar(stage), (uint32_t)C::kStageBytes);
+          const bool ds = DS && tap == p.ds_tap;
+          mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + C::kBBytes * (ds ? 2 : 1)));
           tma_load_4d(sa, &p.map_a[p.tap_map[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
           tma_load_2d(sa + kABytes, &p.map_b, full_bar(stage), tap * p.cin_pad + c0, nt * BN);
+          if (ds) tma_load_2d(sa + kABytes + C::kBBytes, &p.map_b2, full_bar(stage), c0, nt * BN);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::kAccCols);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -237,6 +245,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
             tc_mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (DS) {
+            // the centre tap of a 3x3 / stride 2 / pad 1 filter samples exactly the pixels a 1x1 / stride 2
+            // convolution reads: the block's downsample branch rides on the same A tiles, second accumulator
+            const int tap = kb / p.kchunks;
+            if (tap == p.ds_tap) {
+              const int c = kb - tap * p.kchunks;
+              const uint64_t b2_desc = smem_desc_sw128(sa + kABytes + C::kBBytes);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                tc_mma(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), C::kIdesc, (c | k) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (++stage == C::kStages) {
@@ -270,61 +290,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int wo = twi * p.wb + wbi, ho = thi * p.hb + hbi, img = ng * p.nb + nbi;
       const bool valid = (wo < p.wo) && (ho < p.ho) && (img < p.n);
       const long long pix = ((long long)img * p.ho + ho) * p.wo + wo;
-      __nv_bfloat16* yrow = p.y + pix * p.ldy + nt * BN;
-      const __nv_bfloat16* rrow = p.res ? p.res + pix * p.ldres + nt * BN : nullptr;
-      const float* brow = p.bias + nt * BN;
-
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      // one pass over BN accumulator columns: + bias (+ residual) (ReLU) -> bf16 -> 16-byte stores of the pixel's row
+      auto drain = [&](uint32_t taddr, const float* brow, const __nv_bfloat16* rrow, __nv_bfloat16* yrow, bool relu) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[32];
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c + j));
-            f[j] = __uint_as_float(v[j]) + b4.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-          }
-          if (rrow) {
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c + j));
+              f[j] = __uint_as_float(v[j]) + b4.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            if (rrow) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c + j));
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r4);
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c + j));
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r4);
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 rf = __bfloat1622float2(r2[t]);
-                f[j + 2 * t] += rf.x;
-                f[j + 2 * t + 1] += rf.y;
+                for (int t = 0; t < 4; ++t) {
+                  const float2 rf = __bfloat1622float2(r2[t]);
+                  f[j + 2 * t] += rf.x;
+                  f[j + 2 * t + 1] += rf.y;
+                }
               }
             }
-          }
-          if (p.relu) {
+            if (relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            o.x = *reinterpret_cast<uint32_t*>(&t0);
-            o.y = *reinterpret_cast<uint32_t*>(&t1);
-            o.z = *reinterpret_cast<uint32_t*>(&t2);
-            o.w = *reinterpret_cast<uint32_t*>(&t3);
-            *reinterpret_cast<uint4*>(yrow + c + j) = o;
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              o.x = *reinterpret_cast<uint32_t*>(&t0);
+              o.y = *reinterpret_cast<uint32_t*>(&t1);
+              o.z = *reinterpret_cast<uint32_t*>(&t2);
+              o.w = *reinterpret_cast<uint32_t*>(&t3);
+              *reinterpret_cast<uint4*>(yrow + c + j) = o;
+            }
           }
+          __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
         }
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
-      }
+      };
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols);
+      drain(taddr, p.bias + nt * BN, p.res ? p.res + pix * p.ldres + nt * BN : nullptr, p.y + pix * p.ldy + nt * BN, p.relu != 0);
+      if (DS) drain(taddr + (uint32_t)BN, p.bias2 + nt * BN, nullptr, p.y2 + pix * p.ldy2 + nt * BN, false);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -371,8 +392,10 @@ int pick_bn(int cout) {
 struct TcConvPlan {
   ConvGeom g;
   int bn = 0;
+  bool ds = false;
   TcParams prm;
   __nv_bfloat16* d_w = nullptr;
+  __nv_bfloat16* d_w2 = nullptr;
   int64_t bytes = 0;
   const void* x_ptr = nullptr;
   int n_maps = 0;
@@ -411,7 +434,14 @@ static int encode_a_maps(spk_ctx* ctx, TcConvPlan* p, const void* x) {
   return SPK_OK;
 }
 
-int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, const float* d_bias, TcConvPlan** out) {
+bool tc_conv_ds_fusable(const ConvGeom& g3, const ConvGeom& g1) {
+  return g3.kh == 3 && g3.kw == 3 && g3.stride == 2 && g3.pad == 1 && g1.kh == 1 && g1.kw == 1 && g1.stride == 2 && g1.pad == 0 &&
+         g3.cin == g1.cin && g3.cout == g1.cout && g3.h == g1.h && g3.w == g1.w && g3.ldx == g1.ldx && g3.ho == g1.ho &&
+         g3.wo == g1.wo && g1.relu == 0 && g3.cout % 64 == 0 && g1.ldy % 8 == 0 && tc_conv_supported(g3) && tc_conv_supported(g1);
+}
+
+int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, const float* d_bias, TcConvPlan** out,
+                        const float* w_ds, const float* d_bias_ds, int ldy_ds) {
   if (!tc_conv_supported(g_max)) return fail(ctx, SPK_ERR_UNSUPPORTED, "tcgen05 convolution: unsupported geometry");
   TcConvPlan* p = new TcConvPlan;
   p->g = g_max;
@@ -419,6 +449,11 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
   memset(&p->prm, 0, sizeof p->prm);
   TcParams& prm = p->prm;
   p->bn = pick_bn(g.cout);
+  p->ds = w_ds != nullptr;
+  if (p->ds) p->bn = g.cout % 128 == 0 ? 128 : 64;  // two accumulators per buffer: 4 * BN TMEM columns
+  prm.ds_tap = p->ds ? 4 : -1;                       // (r, s) = (1, 1)
+  prm.bias2 = d_bias_ds;
+  prm.ldy2 = ldy_ds;
   prm.bias = d_bias;
   prm.ho = g.ho;
   prm.wo = g.wo;
@@ -504,13 +539,41 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
       return fail(ctx, SPK_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
     }
   }
+  if (p->ds) {
+    // downsample weights: bf16 [Cout][cin_pad]
+    const size_t k1 = (size_t)prm.cin_pad;
+    std::vector<__nv_bfloat16> w2((size_t)g.cout * k1, __float2bfloat16(0.f));
+    for (int o = 0; o < g.cout; ++o)
+      for (int c = 0; c < g.cin; ++c) w2[(size_t)o * k1 + c] = __float2bfloat16(w_ds[(size_t)o * g.cin + c]);
+    cudaError_t e2 = cudaMalloc(&p->d_w2, w2.size() * 2);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_w2, w2.data(), w2.size() * 2, cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) {
+      tc_conv_plan_destroy(p);
+      return fail(ctx, SPK_ERR_CUDA, "tcgen05 convolution: downsample weight upload: %s", cudaGetErrorString(e2));
+    }
+    p->bytes += (int64_t)w2.size() * 2;
+    cuuint64_t dims[2] = {(cuuint64_t)k1, (cuuint64_t)g.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)k1 * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)p->bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(&prm.map_b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_w2, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      tc_conv_plan_destroy(p);
+      return fail(ctx, SPK_ERR_CUDA, "cuTensorMapEncodeTiled(W downsample) failed: %d", (int)r);
+    }
+  }
   // opt in to the large dynamic shared memory on THIS device (the attribute is per device)
   cudaError_t ea = cudaSuccess;
-  switch (p->bn) {
-    case 256: ea = cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmem); break;
-    case 128: ea = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmem); break;
-    case 64: ea = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem); break;
-    case 32: ea = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::kSmem); break;
+  if (p->ds) {
+    if (p->bn == 128) ea = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128, true>::kSmem);
+    else ea = cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64, true>::kSmem);
+  } else switch (p->bn) {
+    case 256: ea = cudaFuncSetAttribute(conv_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmem); break;
+    case 128: ea = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmem); break;
+    case 64: ea = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem); break;
+    case 32: ea = cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::kSmem); break;
   }
   if (ea != cudaSuccess) {
     tc_conv_plan_destroy(p);
@@ -523,21 +586,22 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
 void tc_conv_plan_destroy(TcConvPlan* p) {
   if (!p) return;
   if (p->d_w) cudaFree(p->d_w);
+  if (p->d_w2) cudaFree(p->d_w2);
   delete p;
 }
 
 int64_t tc_conv_plan_bytes(const TcConvPlan* p) { return p ? p->bytes : 0; }
 
-template <int BN>
+template <int BN, bool DS = false>
 static int launch_bn(spk_ctx* ctx, const TcParams& prm) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, DS>;
   const int grid = std::min(prm.total_tiles, ctx->sm_count);
-  conv_tc_kernel<BN><<<grid, kThreads, C::kSmem, ctx->stream>>>(prm);
+  conv_tc_kernel<BN, DS><<<grid, kThreads, C::kSmem, ctx->stream>>>(prm);
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;
 }
 
-int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y) {
+int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y, void* y_ds) {
   if (n <= 0) return SPK_OK;
   if (n > p->g.n) return fail(ctx, SPK_ERR_CAPACITY, "tcgen05 convolution: batch %d > planned %d", n, p->g.n);
   if (x != p->x_ptr) {
@@ -548,8 +612,11 @@ int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void
   prm.n = n;
   prm.res = (const __nv_bfloat16*)res;
   prm.y = (__nv_bfloat16*)y;
+  prm.y2 = (__nv_bfloat16*)y_ds;
+  if (p->ds && !y_ds) return fail(ctx, SPK_ERR_INVALID, "tcgen05 convolution: fused downsample without an output");
   prm.tiles_img = (n + prm.nb - 1) / prm.nb;
   prm.total_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img * prm.tiles_n;
+  if (p->ds) return p->bn == 128 ? launch_bn<128, true>(ctx, prm) : launch_bn<64, true>(ctx, prm);
   switch (p->bn) {
     case 256: return launch_bn<256>(ctx, prm);
     case 128: return launch_bn<128>(ctx, prm);

@@ -9,6 +9,7 @@
 // and replays the op list on the context's stream for every batch.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -38,6 +39,10 @@ struct Op {
   float* d_scale = nullptr;  // bn_relu: scale [C]
   TcConvPlan* tc = nullptr;
   HaloConvPlan* halo = nullptr;
+  // fused downsample branch (1x1 / stride 2 of the same input, computed by this 3x3 / stride 2 convolution's kernel)
+  int ds_out = -1, ds_off = 0, ds_ld = 0;
+  float* d_bias_ds = nullptr;
+  std::vector<float> ds_w, ds_b;
   uint4* d_stem_w = nullptr;  // fused stem: swizzled bf16 weight tile
   int pool_out = -1, hp = 0, wp = 0, pool_ld = 0;  // fused stem: the max-pool's output
   std::vector<float> w_host;  // [Cout][kh][kw][cin] folded fp32, kept until net_end for the tcgen05 packer
@@ -69,6 +74,7 @@ static void net_free(Net* net) {
     if (op.d_w) cudaFree(op.d_w);
     if (op.d_bias) cudaFree(op.d_bias);
     if (op.d_scale) cudaFree(op.d_scale);
+    if (op.d_bias_ds) cudaFree(op.d_bias_ds);
     if (op.d_stem_w) cudaFree(op.d_stem_w);
     if (op.tc) tc_conv_plan_destroy(op.tc);
     if (op.halo) halo_conv_plan_destroy(op.halo);
@@ -529,6 +535,26 @@ int spk_net_end(spk_ctx* ctx) {
       std::vector<float>().swap(c0.b_host);
     }
   }
+  // ---- downsample fusion: a ResNet block's 1x1 / stride-2 shortcut reads exactly the pixels the centre tap of the
+  // block's 3x3 / stride-2 convolution reads; the pair becomes one launch with two accumulators
+  if (net->precision == SPK_PRECISION_BF16 && !getenv("SPK_NO_DS_FUSION")) {
+    for (size_t i = 0; i + 1 < net->ops.size(); ++i) {
+      Op& a = net->ops[i];      // the shortcut (the host declares it first)
+      Op& b = net->ops[i + 1];  // the 3x3
+      if (a.kind != kOpConv || b.kind != kOpConv || a.in != b.in || a.in_off != b.in_off || a.res >= 0 || b.res >= 0) continue;
+      if (a.impl == SPK_CONV_SIMT || b.impl == SPK_CONV_SIMT || a.out == b.out || a.in == 0) continue;
+      if (net->bufs[(size_t)a.in].dtype != SPK_DTYPE_BF16) continue;
+      ConvGeom ga = a.g, gb = b.g;
+      ga.n = gb.n = net->max_batch;
+      if (!tc_conv_ds_fusable(gb, ga)) continue;
+      b.ds_out = a.out;
+      b.ds_off = a.out_off;
+      b.ds_ld = a.g.ldy;
+      b.ds_w = std::move(a.w_host);
+      b.ds_b = std::move(a.b_host);
+      a.kind = kOpNop;
+    }
+  }
   for (auto& op : net->ops) {
     if (op.kind != kOpConv) continue;
     const ConvGeom& g = op.g;
@@ -552,6 +578,14 @@ int spk_net_end(spk_ctx* ctx) {
         rc = halo_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.halo);
         if (rc) return rc;
         net->bytes += halo_conv_plan_bytes(op.halo);
+      } else if (op.ds_out >= 0) {
+        rc = upload(ctx, op.ds_b.data(), op.ds_b.size(), &op.d_bias_ds);
+        if (rc) return rc;
+        rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc, op.ds_w.data(), op.d_bias_ds, op.ds_ld);
+        if (rc) return rc;
+        net->bytes += tc_conv_plan_bytes(op.tc);
+        std::vector<float>().swap(op.ds_w);
+        std::vector<float>().swap(op.ds_b);
       } else {
         rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc);
         if (rc) return rc;
@@ -596,17 +630,19 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
         ConvGeom g = op.g;
         g.n = (int)n;
         const double px = (double)n * g.ho * g.wo;
+        const double ds_taps = op.ds_out >= 0 ? 1.0 : 0.0;  // the fused 1x1 shortcut: one more tap, one more output
         ProfScope prof(ctx, op.in == 0 ? SPK_PROF_STEM : (op.impl == SPK_CONV_TCGEN05 ? SPK_PROF_CONV_TC : SPK_PROF_CONV_SIMT),
-                       2.0 * px * g.cout * g.kh * g.kw * g.cin,
-                       (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * (op.res >= 0 ? 2 : 1) +
-                           (double)g.cout * g.kh * g.kw * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
+                       2.0 * px * g.cout * (g.kh * g.kw + ds_taps) * g.cin,
+                       (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * ((op.res >= 0 ? 2 : 1) + ds_taps) +
+                           (double)g.cout * (g.kh * g.kw + ds_taps) * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
                        "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
-                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.halo ? " [halo]" : "");
+                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.halo ? " [halo]" : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : ""));
         const void* res = op.res >= 0 ? ptr(op.res, 0) : nullptr;
         if (op.halo)
           rc = halo_conv_launch(ctx, op.halo, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
         else if (op.impl == SPK_CONV_TCGEN05)
-          rc = tc_conv_launch(ctx, op.tc, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
+          rc = tc_conv_launch(ctx, op.tc, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off),
+                              op.ds_out >= 0 ? ptr(op.ds_out, op.ds_off) : nullptr);
         else
           rc = launch_conv_simt(ctx, g, ptr(op.in, op.in_off), bi.dtype, op.d_w, op.d_bias, res, ptr(op.out, op.out_off),
                                 bo.dtype);

@@ -116,10 +116,13 @@ int launch_head(spk_ctx* ctx, const void* act, int act_dtype, int64_t n, int hw,
 // conv_tc.cu (tcgen05 / TMEM / TMA implicit GEMM)
 struct TcConvPlan;
 bool tc_conv_supported(const ConvGeom& g);
+// w_ds / bias_ds / ldy_ds: optional fused 1x1 stride-2 downsample branch (same input, same Cout) of a 3x3 stride-2 conv
+bool tc_conv_ds_fusable(const ConvGeom& g3x3, const ConvGeom& g1x1);
 int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
-                        const float* bias, TcConvPlan** out);
+                        const float* bias, TcConvPlan** out, const float* w_ds = nullptr, const float* bias_ds = nullptr,
+                        int ldy_ds = 0);
 void tc_conv_plan_destroy(TcConvPlan* p);
-int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y);
+int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y, void* y_ds = nullptr);
 int64_t tc_conv_plan_bytes(const TcConvPlan* p);
 // conv_halo.cu (3x3 / stride 1: halo tile resident in shared memory, taps = shifted descriptors, TMA-store epilogue)
 struct HaloConvPlan;

@@ -182,3 +182,66 @@ def test_fused_stem_matches_unfused_and_torch(ctx, t, n):
     mag = max(1.0, float(np.abs(ref).max()))
     assert float(np.abs(fused - ref).max()) <= 4e-3 * mag, float(np.abs(fused - ref).max())
     assert float(np.abs(fused - unfused).max()) <= 2e-2 * mag
+
+
+@pytest.mark.parametrize("t,n,c1,c2", [(56, 5, 64, 128), (28, 9, 128, 256), (14, 33, 256, 512), (45, 3, 64, 128)], ids=lambda v: str(v))
+def test_fused_downsample_shortcut(ctx, t, n, c1, c2):
+    """A ResNet stage entry: the 1x1 / stride-2 shortcut fused into the 3x3 / stride-2 convolution's kernel (second
+    accumulator on the centre tap) against the two separate launches and a torch fp32 reference."""
+    import os
+
+    import torch
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(t + c2)
+    img = rng.integers(0, 256, (n, t, t), dtype=np.uint8)
+    w1 = (rng.standard_normal((c1, 1, 3, 3)) * 0.6).astype(np.float32)
+    w3 = (rng.standard_normal((c2, c1, 3, 3)) * np.sqrt(2.0 / (c1 * 9))).astype(np.float32)
+    wd = (rng.standard_normal((c2, c1, 1, 1)) * np.sqrt(1.0 / c1)).astype(np.float32)
+    b3 = np.linspace(-0.5, 0.5, c2).astype(np.float32)
+    bd = np.linspace(0.3, -0.3, c2).astype(np.float32)
+    lib = ctx.lib
+
+    def run(fused):
+        if fused:
+            os.environ.pop("SPK_NO_DS_FUSION", None)
+        else:
+            os.environ["SPK_NO_DS_FUSION"] = "1"
+        try:
+            ctx.ck(lib.spk_net_begin(ctx.ctx, t, t, 1, _lib.PRECISION_BF16, n))
+            ctx.ck(lib.spk_net_conv(ctx.ctx, 0, 0, 1, 0, -1, w1.ctypes.data, c1, 1, 3, 3, 1, 1, None, None, None, None, BN_EPS, None, 1, _lib.CONV_SIMT))
+            ctx.ck(lib.spk_net_conv(ctx.ctx, 1, 0, 3, 0, -1, wd.ctypes.data, c2, c1, 1, 1, 2, 0, None, None, None, None, BN_EPS, bd.ctypes.data, 0, _lib.CONV_TCGEN05))
+            ctx.ck(lib.spk_net_conv(ctx.ctx, 1, 0, 2, 0, -1, w3.ctypes.data, c2, c1, 3, 3, 2, 1, None, None, None, None, BN_EPS, b3.ctypes.data, 1, _lib.CONV_TCGEN05))
+            hw = np.zeros((4, c2), np.float32)
+            hb = np.zeros(4, np.float32)
+            ctx.ck(lib.spk_net_head(ctx.ctx, 2, 1, (C.c_void_p * 1)(hw.ctypes.data), (C.c_void_p * 1)(hb.ctypes.data), (C.c_int * 2)(c2, 4)))
+            ctx.ck(lib.spk_net_end(ctx.ctx))
+        finally:
+            os.environ.pop("SPK_NO_DS_FUSION", None)
+        launches0 = lib.spk_launch_count(ctx.ctx)
+        with torch.cuda.device(ctx.device), torch.cuda.stream(ctx.stream):
+            x = torch.from_numpy(img).to(ctx.device)
+            probs = torch.empty((n, 4), dtype=torch.float32, device=ctx.device)
+            ctx.ck(lib.spk_forward(ctx.ctx, x.data_ptr(), n, 0.0, None, probs.data_ptr(), None, None))
+            ctx.sync()
+        outs = []
+        for buf in (1, 2, 3):
+            h, w, c = C.c_int(), C.c_int(), C.c_int()
+            ctx.ck(lib.spk_net_read_buffer(ctx.ctx, buf, n, None, 0, C.byref(h), C.byref(w), C.byref(c)))
+            out = np.empty((n, h.value, w.value, c.value), np.float32)
+            ctx.ck(lib.spk_net_read_buffer(ctx.ctx, buf, n, out.ctypes.data, out.size, C.byref(h), C.byref(w), C.byref(c)))
+            outs.append(out)
+        return outs, lib.spk_launch_count(ctx.ctx) - launches0
+
+    (a_f, y_f, d_f), launches_f = run(True)
+    (a_u, y_u, d_u), launches_u = run(False)
+    assert launches_f == launches_u - 1  # one launch fewer
+    assert np.array_equal(a_f, a_u)
+    x = torch.from_numpy(a_f).permute(0, 3, 1, 2)
+    ref3 = F.relu(F.conv2d(x, torch.from_numpy(_bf16(w3)), torch.from_numpy(b3), stride=2, padding=1)).permute(0, 2, 3, 1).numpy()
+    refd = F.conv2d(x, torch.from_numpy(_bf16(wd)), torch.from_numpy(bd), stride=2).permute(0, 2, 3, 1).numpy()
+    for got, sep, ref in ((y_f, y_u, ref3), (d_f, d_u, refd)):
+        assert got.shape == ref.shape == sep.shape
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert float(np.abs(got - ref).max()) <= 6e-3 * scale
+        assert float(np.abs(got - sep).max()) <= 6e-3 * scale
