@@ -132,6 +132,14 @@ int halo_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oi
 void halo_conv_plan_destroy(HaloConvPlan* p);
 int halo_conv_launch(spk_ctx* ctx, HaloConvPlan* p, int n, const void* x, const void* res, void* y);
 int64_t halo_conv_plan_bytes(const HaloConvPlan* p);
+// conv_pair.cu (Cout >= 128: CTA pairs, tcgen05.mma.cta_group::2, each CTA stages half of the weight tile)
+struct PairConvPlan;
+bool pair_conv_supported(const ConvGeom& g);
+int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
+                          const float* bias, PairConvPlan** out);
+void pair_conv_plan_destroy(PairConvPlan* p);
+int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y);
+int64_t pair_conv_plan_bytes(const PairConvPlan* p);
 // stem.cu: conv 7x7/2 (1 gray plane -> 64) + bias + ReLU + maxpool 3x3/2 fused on tcgen05; u8 in -> bf16 NHWC out
 bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int pool_pad);
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w_folded /*[64][7][7]*/, uint4** d_out);

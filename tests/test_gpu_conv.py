@@ -91,7 +91,7 @@ GEOMS = [
     (30, 3, 64, 128, 3, 1, 1, True, False),     # Cin 64 -> Cout 128, 4-row tiles with a 2-row remainder
     (28, 2, 64, 192, 3, 1, 1, True, True),      # three N tiles of 64
 ]
-HALO_GEOMS = [0, 1, 10, 12]  # also run through the tap-per-TMA kernel (SPK_CONV_TCGEN05_TAPS)
+HALO_GEOMS = [0, 1, 10, 12, 2, 4, 5, 9]  # halo / pair geometries also run through the tap-per-TMA kernel (SPK_CONV_TCGEN05_TAPS)
 
 
 @pytest.mark.parametrize("gi", HALO_GEOMS, ids=[f"g{i}" for i in HALO_GEOMS])
