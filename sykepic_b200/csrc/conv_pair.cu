@@ -22,7 +22,7 @@
 //     producer warp; the "accumulator drained" barrier lives in the leader and counts the epilogue warps of
 //     both CTAs (remote mbarrier.arrive).
 // Persistent clusters (74 x 2 CTAs), warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocation +
-// MMA issuer (leader only), warp 2 = residual producer, warps 3-6 = epilogue.
+// MMA issuer (leader only), warp 2 = residual producer, warps 3-10 = epilogue.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -34,7 +34,9 @@ namespace spk {
 namespace {
 using namespace tc;
 
-constexpr int kThreads = 224;
+constexpr int kEpiWarps = 8;  // two per TMEM lane quarter, 32 of a slab's 64 channels each
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 96 + kEpiThreads;
 constexpr int kBK = 64;
 constexpr int kMaxTaps = 9;
 constexpr int kABytes = 128 * kBK * 2;
@@ -52,6 +54,7 @@ struct alignas(64) PairParams {
   int m_tiles, units;
   int taps, kchunks, cin_pad;
   int stages, res_slots;
+  long long* trace;  // debug (SPK_PAIR_TRACE=1): clock64 stamps of one CTA's epilogue thread 0
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
 
@@ -70,17 +73,20 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// remote arrive.  CTA-scope release (the default) is enough: what the barrier orders are tcgen05.ld reads of
+// TMEM, which tcgen05.fence::before_thread_sync orders; a .release.cluster arrive was measured at ~1500
+// cycles per call here (it drains the thread's outstanding shared / global stores cluster-wide).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait with cluster-scope acquire (the arrivals come from both CTAs)
+// wait on a barrier whose arrivals come from both CTAs
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity), "r"(1000000u)
@@ -167,9 +173,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(r_full(s), 1);
-      mbar_init(r_empty(s), 4);
-      mbar_init(t_full(s), 1);   // multicast tcgen05.commit
-      mbar_init(t_empty(s), 8);  // used in the leader only: the epilogue warps of both CTAs
+      mbar_init(r_empty(s), kEpiWarps);
+      mbar_init(t_full(s), 1);               // multicast tcgen05.commit
+      mbar_init(t_empty(s), 2 * kEpiWarps);  // used in the leader only: the epilogue warps of both CTAs
     }
     mbar_init_fence();
     tma_prefetch_desc(&p.map_a[0]);
@@ -279,48 +285,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
       }
     }
   } else {
-    // ===== epilogue: warps 3-6; warp w may touch TMEM lanes [32 * (w % 4), +32) =====
+    // ===== epilogue: warps 3-10; warp w may touch TMEM lanes [32 * (w % 4), +32) and takes channels
+    // [32 * half, +32) of every 64-channel slab =====
     const int q = warp & 3;
+    const int half = (warp - 3) >> 2;
     const int et = threadIdx.x - 96;
     const int row = q * 32 + lane;  // TMEM lane == pixel of the box == row of the staging tile
     const uint32_t sw = (uint32_t)(row & 7);
     int acc = 0, rs = 0, os = 0;
     uint32_t accph = 0, rph = 0;
+    int tr = 0;
+    const bool tracing = p.trace != nullptr && blockIdx.x == 10 && et == 0;
+#define PAIR_TRACE() do { if (tracing && tr < 250) p.trace[tr++] = clock64(); } while (0)
     for (int u = cluster_id; u < p.units; u += n_clusters) {
       int nt, w0, h0, n0;
       decode(u, nt, w0, h0, n0);
+      PAIR_TRACE();
       mbar_wait(t_full(acc), accph);
       tc_fence_after();
+      PAIR_TRACE();
 #pragma unroll 1
       for (int slab = 0; slab < kSlabs; ++slab) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * 64);
-        uint32_t v0[32], v1[32];
-        tmem_ld32(taddr, v0);
-        tmem_ld32(taddr + 32, v1);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * 64 + half * 32);
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
         tmem_ld_wait();
         if (slab == kSlabs - 1) {  // accumulator buffer drained: tell the leader's MMA thread
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_rank(t_empty(acc), 0));
         }
+        PAIR_TRACE();
         if (et == 0) tma_store_wait_read<1>();  // staging slot `os` was last read by the store issued two slabs ago
+        PAIR_TRACE();
         if (p.has_res) mbar_wait(r_full(rs), rph);
-        named_bar_sync(1, 128);
+        PAIR_TRACE();
+        named_bar_sync(1, kEpiThreads);
+        PAIR_TRACE();
         {
-          const float* bsm = bias_sm + nt * BN + slab * 64;
+          const float* bsm = bias_sm + nt * BN + slab * 64 + half * 32;
           unsigned char* orow_p = gen + out_off + (uint32_t)os * kIoSlot + (uint32_t)row * 128u;
           const unsigned char* rrow_p = gen + res_off + (uint32_t)rs * kIoSlot + (uint32_t)row * 128u;
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
+          for (int c4 = 0; c4 < 4; ++c4) {
             float f[8];
-            const float4 ba = *reinterpret_cast<const float4*>(bsm + c8 * 8), bb = *reinterpret_cast<const float4*>(bsm + c8 * 8 + 4);
+            const float4 ba = *reinterpret_cast<const float4*>(bsm + c4 * 8), bb = *reinterpret_cast<const float4*>(bsm + c4 * 8 + 4);
             const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int col = c8 * 8 + e;
-              f[e] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]) + bv[e];
-            }
-            const uint32_t chunk = ((uint32_t)c8 ^ sw) << 4;
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c4 * 8 + e]) + bv[e];
+            const uint32_t chunk = ((uint32_t)(half * 4 + c4) ^ sw) << 4;
             if (p.has_res) {
               const uint4 r4 = *reinterpret_cast<const uint4*>(rrow_p + chunk);
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r4);
@@ -355,8 +368,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
             rph ^= 1u;
           }
         }
+        PAIR_TRACE();
         fence_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(2, kEpiThreads);
+        PAIR_TRACE();
         if (et == 0) {
           tma_store_4d(&p.map_y, base + out_off + (uint32_t)os * kIoSlot, nt * BN + slab * 64, w0, h0, n0);
           tma_store_commit();
@@ -558,11 +573,30 @@ int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const 
   prm.m_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img;
   prm.units = ((prm.m_tiles + 1) / 2) * prm.tiles_n;
   const int clusters = std::min(prm.units, ctx->sm_count / 2);
+  static const bool want_trace = getenv("SPK_PAIR_TRACE") != nullptr;
+  static long long* d_trace = nullptr;
+  static int trace_left = 4;
+  prm.trace = nullptr;
+  if (want_trace && trace_left > 0 && prm.kchunks * prm.taps <= 2) {
+    if (!d_trace) cudaMalloc(&d_trace, 256 * sizeof(long long));
+    cudaMemsetAsync(d_trace, 0, 256 * sizeof(long long), ctx->stream);
+    prm.trace = d_trace;
+  }
   if (p->bn == 256)
     conv_pair_kernel<256><<<2 * clusters, kThreads, p->smem, ctx->stream>>>(prm);
   else
     conv_pair_kernel<128><<<2 * clusters, kThreads, p->smem, ctx->stream>>>(prm);
   SPK_LAUNCH_CHECK(ctx);
+  if (prm.trace) {
+    --trace_left;
+    long long h[256];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "pair trace BN=%d cin=%d cout=%d res=%d stages=%d units=%d (per unit: start, t_full; per slab: ld done, store-read wait, r_full, bar1, math done, bar2):\n ",
+            p->bn, g.cin, g.cout, prm.has_res, prm.stages, prm.units);
+    for (int i = 0; i < 250 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+    fprintf(stderr, "\n");
+  }
   return SPK_OK;
 }
 
