@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--arch", default="resnet18")
     ap.add_argument("--batch", type=int, default=None, help="ROIs per step per GPU (default 256; 512 for resnet50/densenet121)")
+    ap.add_argument("--chunk-batches", type=int, default=16,
+                    help="batches per bin chunk: K1 decodes a chunk per launch (as Engine.run_bin_device does), K2+K3 run per batch")
     ap.add_argument("--target", type=int, default=224)
     ap.add_argument("--precision", choices=("bf16", "fp32"), default="bf16")
     ap.add_argument("--conv-impl", choices=("auto", "simt", "tcgen05", "taps"), default="auto")
@@ -63,15 +65,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def workload(args, seed, n_batches):
-    """n_batches batches of `batch` non-empty synthetic ROIs -> list of (w, h, start, roi_bytes)."""
+def workload(args, seed, n_chunks, rois=None):
+    """n_chunks synthetic bins of `rois` non-empty ROIs (default: one batch) -> list of (w, h, start, roi_bytes)."""
     from sykepic_b200 import synth
 
+    rois = rois or args.batch
     out = []
-    for i in range(n_batches):
-        b = synth.synth_bin(seed + i, int(args.batch * 1.01) + 8)
-        keep = np.flatnonzero(b["w"] > 0)[: args.batch]
-        assert len(keep) == args.batch
+    for i in range(n_chunks):
+        b = synth.synth_bin(seed + i, int(rois * 1.01) + 8)
+        keep = np.flatnonzero(b["w"] > 0)[:rois]
+        assert len(keep) == rois
         out.append((b["w"][keep].astype(np.int32), b["h"][keep].astype(np.int32), b["start"][keep].astype(np.int64), b["roi_bytes"]))
     return out
 
@@ -232,30 +235,39 @@ def run_b200(args):
 
     tmp = tempfile.mkdtemp(prefix=f"spk_bench_r{rank}_")
     mdir = model_dir(args, tmp)
-    eng = engine.Engine(mdir, device=local, precision=args.precision, max_batch=args.batch, conv_impl=args.conv_impl)
+    G = max(1, args.chunk_batches)
+    chunk = G * args.batch
+    eng = engine.Engine(mdir, device=local, precision=args.precision, max_batch=args.batch, conv_impl=args.conv_impl, pre_chunk=chunk)
     thr = {name: 0.5 for name in eng.spec.classes}
     eng.set_thresholds(thr)
-    n_pool = 8
-    batches = workload(args, 2000 + 100 * rank, n_pool)
-    in_bytes = [int((b[0].astype(np.int64) * b[1]).sum()) for b in batches]
+    n_pool = 3
+    # synthetic bins of `chunk` ROIs: the engine decodes a whole chunk of a bin per K1 launch and walks it in batches
+    chunks = workload(args, 2000 + 100 * rank, n_pool, chunk)
+    in_bytes = [int((b[0].astype(np.int64) * b[1]).sum()) for b in chunks]
     K = eng.k
 
     # ---- device-resident inputs (value) and pinned host inputs (e2e)
     stream = eng.stream
     dev_in = []
     with torch.cuda.stream(stream):
-        for w, h, start, roi in batches:
+        for w, h, start, roi in chunks:
             dev_in.append((torch.from_numpy(roi).to(dev), torch.from_numpy(start).to(dev), torch.from_numpy(w).to(dev),
                            torch.from_numpy(h).to(dev), len(roi)))
-        probs = torch.empty((args.batch, K), dtype=torch.float32, device=dev)
-        label = torch.empty(args.batch, dtype=torch.int32, device=dev)
-        cls = torch.empty(args.batch, dtype=torch.uint8, device=dev)
+        probs = torch.empty((chunk, K), dtype=torch.float32, device=dev)
+        label = torch.empty(chunk, dtype=torch.int32, device=dev)
+        cls = torch.empty(chunk, dtype=torch.uint8, device=dev)
         flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream.synchronize()
 
     def step_device(i):
-        roi_d, start_d, w_d, h_d, roi_len = dev_in[i % n_pool]
-        eng.run_bin_device(roi_d, roi_len, start_d, w_d, h_d, args.batch, probs, label, cls)
+        """One batch through K2 + K3; every G-th step first runs K1 on the next chunk of G batches (all of K1's work
+        for the ROIs of the timed steps is inside the timed region)."""
+        j = i % G
+        if j == 0:
+            roi_d, start_d, w_d, h_d, roi_len = dev_in[(i // G) % n_pool]
+            eng.preprocess(roi_d, roi_len, start_d, w_d, h_d, chunk, eng._x)
+        lo = j * args.batch
+        eng.forward(eng._x[lo:lo + args.batch], args.batch, probs[lo:lo + args.batch], label[lo:lo + args.batch], cls[lo:lo + args.batch])
 
     def barrier():
         if world > 1:
@@ -275,43 +287,43 @@ def run_b200(args):
         return sum(a.elapsed_time(b) for a, b in evs)
 
     with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            step_device(i)
+        for i in range(max(args.warmup, 1)):
+            step_device(i)  # step 0 decodes chunk 0
     launches0 = eng.launches
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     wall0 = time.perf_counter()
-    ms_total = timed(step_device, args.steps)
+    ms_total = timed(step_device, args.steps)  # starts at step 0 again: K1 runs ceil(steps / G) times inside
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     gpu_launches = eng.launches - launches0
     assert eng.fault_count() == 0
 
-    # ---- e2e: host API, pinned host buffers, H2D + D2H inside the timed region
-    host_in = [(w, h, start, torch.from_numpy(roi).pin_memory().numpy()) for w, h, start, roi in batches]
-    ids = np.arange(args.batch, dtype=np.int32)
+    # ---- e2e: host API on whole chunks (a bin is what the API takes), pinned host buffers, H2D + D2H inside the timed region
+    host_in = [(w, h, start, torch.from_numpy(roi).pin_memory().numpy()) for w, h, start, roi in chunks]
+    ids = np.arange(chunk, dtype=np.int32)
 
-    def step_host(i):
+    def call_host(i):
         w, h, start, roi = host_in[i % n_pool]
         eng.run_rois(ids, w, h, start, roi, want_labels=True)
 
-    for i in range(args.warmup):
-        step_host(i)
+    call_host(0)
     barrier()
-    e2e_steps = args.steps
+    e2e_calls = max(1, -(-args.steps // G))
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        step_host(i)
+    for i in range(e2e_calls):
+        call_host(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
-    h2d = int(np.mean(in_bytes)) + args.batch * 16
+    e2e_steps = e2e_calls * G
+    h2d = (int(np.mean(in_bytes)) + chunk * 16) // G
     d2h = args.batch * (K * 4 + 4 + 1)
 
     # ---- roofline pass: per-launch CUDA events on the engine's stream (separate pass, same inputs)
-    prof_steps = max(3, min(10, args.steps))
+    prof_steps = G  # one full chunk cycle: K1 once, K2 + K3 G times
     eng.profile_begin()
     with torch.cuda.stream(stream):
         for i in range(prof_steps):
@@ -363,7 +375,8 @@ def run_b200(args):
             pre_bytes = pre["bytes"] + mean_in * pre["launches"]
             g = pre_bytes / (pre["ms"] * 1e-3) / 1e9
             pre_roof = {"bound": "hbm", "kernel": "preprocess_kernel", "achieved": g, "peak": float(pk["hbm_gbs"]), "unit": "GB/s",
-                        "frac": g / float(pk["hbm_gbs"]), "bytes_per_roi": pre_bytes / (pre["launches"] * args.batch)}
+                        "frac": g / float(pk["hbm_gbs"]), "bytes_per_roi": pre_bytes / (pre["launches"] * chunk),
+                        "rois_per_launch": chunk, "ms_per_launch": pre["ms"] / pre["launches"]}
         value = args.gpus * args.batch * args.steps / (ms_total * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -374,10 +387,11 @@ def run_b200(args):
                        "arch": args.arch, "batch_per_gpu": args.batch, "target": args.target, "conv_impl": args.conv_impl,
                        "parallelism": f"bins sharded over {args.gpus} GPU(s), no collective",
                        "l2": "flushed between steps (256 MiB memset outside the timed events)",
-                       "mean_roi_bytes": mean_in / args.batch,
+                       "mean_roi_bytes": mean_in / chunk,
+                       "k1_chunk": f"K1 decodes {chunk} ROIs ({G} batches) per launch, every {G}th step; K2+K3 per batch",
                        "conv_gflop_per_roi_logical": CONV_GFLOP.get(args.arch) if args.target == 224 else None},
             "e2e": {"value": args.gpus * args.batch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "Engine.run_rois (host numpy/pinned in, host numpy out)"},
+                    "d2h_bytes_per_step": d2h, "api": f"Engine.run_rois on bins of {chunk} ROIs (host pinned in, host numpy out), {e2e_calls} calls"},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -386,7 +400,7 @@ def run_b200(args):
             "wall_s_timed_region": wall,
         }
         if not args.no_cpu_baseline:
-            rate, n_done, cores = cpu_port_rate(args, mdir, batches, args.cpu_seconds)
+            rate, n_done, cores = cpu_port_rate(args, mdir, chunks, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_done} ROIs of the same synthetic batch (oracle: numpy transform + torch-CPU fp32 forward)",
                                     "host_cpus": os.cpu_count()}

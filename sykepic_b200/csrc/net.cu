@@ -182,6 +182,8 @@ int spk_destroy(spk_ctx* ctx) {
   net_free(ctx->net);
   if (ctx->d_faults) cudaFree(ctx->d_faults);
   if (ctx->d_default_lut) cudaFree(ctx->d_default_lut);
+  if (ctx->d_big_list) cudaFree(ctx->d_big_list);
+  if (ctx->d_big_count) cudaFree(ctx->d_big_count);
   delete ctx;
   return SPK_OK;
 }

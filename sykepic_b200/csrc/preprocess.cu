@@ -13,7 +13,11 @@
 // (the histogram pass uses 16-byte loads; the horizontal pass re-reads them through L1/L2),
 // horizontally interpolated source rows are staged in shared memory as u16, and every output
 // pixel is written exactly once with 16-byte stores.
+#include <cooperative_groups.h>
+
 #include "spk_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace spk {
 namespace {
@@ -39,6 +43,9 @@ struct Params {
   void* out;
   unsigned long long* faults;
   int slabs;
+  int* big_list;        // u8 path: ROIs over `big_bytes` are queued here by the warp kernel ...
+  unsigned* big_count;  // ... and resized by clusters of kBigSlabs CTAs (preprocess_big_kernel)
+  long long big_bytes;
 };
 
 // OpenCV: f = float((d + 0.5) * scale - 0.5); s = floor(f); f -= s.  No FMA contraction allowed.
@@ -135,20 +142,24 @@ __device__ __forceinline__ void store4_u8(const Params& p, long long n, int r, i
   }
 }
 
-__global__ void __launch_bounds__(kThreads) preprocess_kernel(Params p) {
+// One (ROI, slab of output rows) per CTA of kThreads threads.  kCluster: the CTAs of a thread-block cluster hold the
+// slabs of one ROI; each histograms 1/slabs of the ROI bytes and the partial histograms are summed through
+// distributed shared memory (otherwise every slab CTA histograms the whole ROI).
+template <bool kCluster>
+__device__ __forceinline__ void roi_slab(const Params& p, const long long n, const int slab) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   unsigned short* hbuf = reinterpret_cast<unsigned short*>(dyn_smem);  // [hrows][new_w]
   __shared__ unsigned hist[kWarps][256];
+  __shared__ unsigned hist_cta[256];
   __shared__ Tables tb;
   __shared__ float lut_s[3 * 256];
   __shared__ int s_mode;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long n = blockIdx.x / p.slabs;
-  const int slab = blockIdx.x % p.slabs;
   const int th = p.th, tw = p.tw;
 
-  for (int i = tid; i < 3 * 256; i += kThreads) lut_s[i] = p.lut[i];
+  if (p.out_dtype != SPK_DTYPE_U8)
+    for (int i = tid; i < 3 * 256; i += kThreads) lut_s[i] = p.lut[i];
 
   const int w = p.w[n], h = p.h[n];
   const long long start = p.start[n];
@@ -177,18 +188,27 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(Params p) {
 
   // ---- border value: 256-bin histogram of the ORIGINAL ROI, lowest value wins ties ----------
   int border = p.border_mode == SPK_BORDER_WHITE ? 255 : 0;
-  if (p.border_mode == SPK_BORDER_MODE && valid && has_border) {
+  if (p.border_mode == SPK_BORDER_MODE && valid && (has_border || kCluster)) {
     for (int i = tid; i < kWarps * 256; i += kThreads) (&hist[0][0])[i] = 0;
     __syncthreads();
     const long long total = (long long)w * h;
+    // this CTA's share of the ROI bytes: everything, or the slab-th part in 16-byte units (cluster)
+    long long lo = 0, hi = total;
+    if (kCluster) {
+      const long long per = (((total + p.slabs - 1) / p.slabs) + 15) & ~15LL;
+      lo = min(total, per * slab);
+      hi = min(total, lo + per);
+    }
     unsigned* my = hist[warp];
+    const uint8_t* part = src + lo;
+    const long long part_total = hi - lo;
     // unaligned head, 16-byte body, tail
-    const unsigned long long addr = (unsigned long long)src;
+    const unsigned long long addr = (unsigned long long)part;
     long long head = (long long)((16 - (addr & 15)) & 15);
-    if (head > total) head = total;
-    for (long long i = tid; i < head; i += kThreads) atomicAdd(&my[src[i]], 1u);
-    const long long nvec = (total - head) / 16;
-    const uint4* v4 = reinterpret_cast<const uint4*>(src + head);
+    if (head > part_total) head = part_total;
+    for (long long i = tid; i < head; i += kThreads) atomicAdd(&my[part[i]], 1u);
+    const long long nvec = (part_total - head) / 16;
+    const uint4* v4 = reinterpret_cast<const uint4*>(part + head);
     for (long long i = tid; i < nvec; i += kThreads) {
       uint4 q = __ldg(v4 + i);
       unsigned wds[4] = {q.x, q.y, q.z, q.w};
@@ -200,12 +220,20 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(Params p) {
         atomicAdd(&my[wds[j] >> 24], 1u);
       }
     }
-    for (long long i = head + nvec * 16 + tid; i < total; i += kThreads) atomicAdd(&my[src[i]], 1u);
+    for (long long i = head + nvec * 16 + tid; i < part_total; i += kThreads) atomicAdd(&my[part[i]], 1u);
     __syncthreads();
     // 256 threads: one bin each, then argmax with the lowest index winning ties
     unsigned cnt = 0;
 #pragma unroll
     for (int k = 0; k < kWarps; ++k) cnt += hist[k][tid];
+    if (kCluster) {
+      cg::cluster_group cluster = cg::this_cluster();
+      hist_cta[tid] = cnt;
+      cluster.sync();
+      cnt = 0;
+      for (int r = 0; r < p.slabs; ++r) cnt += cluster.map_shared_rank(hist_cta, r)[tid];
+      cluster.sync();  // nobody leaves (or overwrites hist_cta) while a peer still reads it
+    }
     // pack (count, 255 - bin) so that max picks the highest count, then the lowest bin
     unsigned long long key = ((unsigned long long)cnt << 8) | (unsigned)(255 - tid);
 #pragma unroll
@@ -348,6 +376,374 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(Params p) {
   }
 }
 
+
+
+__global__ void __launch_bounds__(kThreads) preprocess_kernel(Params p) {
+  roi_slab<false>(p, blockIdx.x / p.slabs, blockIdx.x % p.slabs);
+}
+
+// u8 path, ROIs over p.big_bytes (the ~1 % heavy tail of IFCB ROIs, up to 1380x1034): one cluster of kBigSlabs CTAs per
+// queued ROI, looping over the queue the warp kernel filled.
+constexpr int kBigSlabs = 8;
+constexpr int kBigClusters = 74;  // 592 CTAs = 4 per SM
+constexpr long long kBigBytes = 24 * 1024;  // ROIs over this many bytes go to the cluster kernel
+
+__global__ void __cluster_dims__(kBigSlabs, 1, 1) __launch_bounds__(kThreads) preprocess_big_kernel(Params p) {
+  const unsigned count = *p.big_count;
+  const int slab = blockIdx.x % kBigSlabs;
+  for (unsigned i = blockIdx.x / kBigSlabs; i < count; i += gridDim.x / kBigSlabs) {
+    roi_slab<true>(p, p.big_list[i], slab);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// u8 fast path (the engine's path): ONE WARP PER ROI, every lane owns 8 adjacent output columns.
+//   * The ROI bytes are read from HBM once, with 16-byte loads, into a per-warp shared-memory stage
+//     (ROIs over kStage bytes -- ~5 % of IFCB ROIs -- are re-read through L1/L2 instead) while the
+//     256-bin histogram of the mode border is built (4 lane-interleaved sub-histograms of packed
+//     16-bit counters, flushed into per-lane 32-bit totals every kHistSeg bytes).
+//   * A lane keeps the two horizontally interpolated source rows of its 8 columns in registers and
+//     walks down the output rows (the vertical taps of a column only need that column), so there is
+//     no intermediate buffer and no block-wide barrier; rows are written with 8-byte stores, the
+//     border rows above/below the image with 16-byte stores.
+// Algorithmic HBM bytes per ROI: w*h read + 16 B descriptor + T*T written.
+constexpr int kWarpsPerCta = 4;
+constexpr int kStage = 8192;           // staged ROI bytes per warp
+constexpr int kCols = 8;               // output columns per lane
+constexpr int kHistSeg = 128 * 1024;   // bytes per histogram segment: <= 4 sub-histograms * 32767 per packed counter
+
+struct RowCoef {
+  int sy;   // un-clamped source row of the first vertical tap
+  int b01;  // b0 | b1 << 16
+};
+
+__device__ __forceinline__ RowCoef row_coef(int dy, double scale_y) {
+  int s;
+  float f;
+  src_coord(dy, scale_y, &s, &f);
+  RowCoef r;
+  r.sy = s;
+  r.b01 = coef(__fsub_rn(1.0f, f)) | (coef(f) << 16);
+  return r;
+}
+
+__device__ __forceinline__ void warp_fill(uint8_t* dst, long long bytes, int value, int lane) {
+  if (bytes <= 0) return;
+  const unsigned long long a = (unsigned long long)dst;
+  long long head = (long long)((16 - (a & 15)) & 15);
+  if (head > bytes) head = bytes;
+  if (lane < head) dst[lane] = (uint8_t)value;
+  const unsigned v4 = (unsigned)value * 0x01010101u;
+  const uint4 q = make_uint4(v4, v4, v4, v4);
+  uint4* body = reinterpret_cast<uint4*>(dst + head);
+  const long long nvec = (bytes - head) >> 4;
+  for (long long i = lane; i < nvec; i += 32) body[i] = q;
+  const long long done = head + (nvec << 4);
+  if (lane < bytes - done) dst[done + lane] = (uint8_t)value;
+}
+
+// The ROI bytes as seen by one warp: its shared-memory stage (32-bit addresses) or global memory.
+template <bool kShared>
+struct SrcView {
+  unsigned sbase;    // shared address of ROI byte 0
+  const uint8_t* g;  // global address of ROI byte 0
+  // 8 bytes starting at ROI offset `off` (any alignment): three aligned words, funnel-shifted
+  __device__ __forceinline__ void window(int off, unsigned* lo, unsigned* hi) const {
+    unsigned w0, w1, w2, sh;
+    if constexpr (kShared) {
+      const unsigned a = sbase + (unsigned)off, al = a & ~3u;
+      sh = a * 8u;  // shf.r.wrap uses the low 5 bits: (a & 3) * 8
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(al));
+      asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(al));
+      asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(al));
+    } else {
+      const unsigned long long a = (unsigned long long)(g + off);
+      const unsigned* al = reinterpret_cast<const unsigned*>(a & ~3ull);
+      sh = (unsigned)a * 8u;
+      w0 = __ldg(al);
+      w1 = __ldg(al + 1);
+      w2 = __ldg(al + 2);
+    }
+    *lo = __funnelshift_r(w0, w1, sh);
+    *hi = __funnelshift_r(w1, w2, sh);
+  }
+};
+
+// Image rows [dy_lo, dy_hi) of one up-scaled (or mildly down-scaled) ROI for the 8
+// columns starting at output column x0.  Per source row a lane loads two 8-byte windows (columns 0-3 and 4-7);
+// PRMT picks each tap pair out of its window and DP2A does S0*a0 + S1*a1.  The vertical pass is done on pixel
+// pairs: PRMT gathers the high halves of two 32-bit products, so the fma and alu pipes stay balanced.
+template <bool kShared>
+__device__ __forceinline__ void image_rows_fast(const SrcView<kShared> S, int w, int h, int nw, int nh, int dy_lo, int dy_hi, int tw,
+                                                int left, int border,
+                                                int x0, uint8_t* __restrict__ out_rows /* row `top`, column 0 */, bool aligned8,
+                                                uint4* rowrec /* 32 records of this warp, shared */, int lane) {
+  const int count = min(kCols, tw - x0);
+  const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)nw, (double)w));
+  const double scale_y = __ddiv_rn(1.0, __ddiv_rn((double)nh, (double)h));
+  unsigned a01[kCols];  // a0 | a1 << 16 (both in [0, 2048])
+  unsigned sel[kCols];  // PRMT selector of the tap pair within the window of the column's group
+  int smin[2];
+  unsigned keep[2] = {0u, 0u};  // byte mask of the image columns of each 4-column group (the others are left / right border)
+#pragma unroll
+  for (int i = 0; i < kCols; ++i) {
+    int s;
+    float f;
+    const int dx = x0 + i - left;
+    if (dx >= 0 && dx < nw) keep[i >> 2] |= 0xffu << (8 * (i & 3));
+    src_coord(min(max(dx, 0), nw - 1), scale_x, &s, &f);  // border columns repeat the nearest image column (then masked)
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= w - 1) { s = w - 1; f = 0.f; }
+    const unsigned a1 = (unsigned)coef(f);
+    a01[i] = (unsigned)coef(__fsub_rn(1.0f, f)) | (a1 << 16);
+    if ((i & 3) == 0) smin[i >> 2] = s;
+    const unsigned k0 = (unsigned)(s - smin[i >> 2]);
+    sel[i] = k0 | ((k0 + (a1 ? 1u : 0u)) << 4);  // a zero weight never reads its tap (cv2 clamps it instead)
+  }
+  int H0[kCols], H1[kCols];
+  auto hrow = [&](int roff, int* H) {
+    unsigned lo, hi;
+    S.window(roff + smin[0], &lo, &hi);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) H[i] = (int)(__dp2a_lo(a01[i], __byte_perm(lo, hi, sel[i]), 0u) >> 4);
+    S.window(roff + smin[1], &lo, &hi);
+#pragma unroll
+    for (int i = 4; i < 8; ++i) H[i] = (int)(__dp2a_lo(a01[i], __byte_perm(lo, hi, sel[i]), 0u) >> 4);
+  };
+  uint8_t* dst = out_rows + x0;
+  const unsigned bword = (unsigned)border * 0x01010101u;
+  const bool full = aligned8 && count == kCols;
+  int py0 = -1, py1 = -1;  // source rows of the previous output row (warp-uniform)
+  for (int base = dy_lo; base < dy_hi; base += 32) {
+    // lane L prepares output row base+L: vertical weights, source rows, and what has to be (re)loaded; the warp then
+    // reads one row record per output row from its shared scratch (a broadcast load, cheaper than shuffles)
+    const RowCoef mine = row_coef(base + lane, scale_y);
+    const int y0 = min(max(mine.sy, 0), h - 1), y1 = min(max(mine.sy + 1, 0), h - 1);
+    int q0 = __shfl_up_sync(0xffffffffu, y0, 1), q1 = __shfl_up_sync(0xffffffffu, y1, 1);
+    if (lane == 0) { q0 = py0; q1 = py1; }
+    const unsigned code = (y0 == q0 && y1 == q1) ? 0u : (y0 == q1 ? 1u : 2u);  // 0 keep, 1 shift + load y1, 2 load both
+    py0 = __shfl_sync(0xffffffffu, y0, 31);
+    py1 = __shfl_sync(0xffffffffu, y1, 31);
+    __syncwarp();
+    rowrec[lane] = make_uint4((unsigned)(y1 * w), (unsigned)mine.b01, code, (unsigned)(y0 * w));
+    __syncwarp();
+    const int rows = min(32, dy_hi - base);
+    for (int j = 0; j < rows; ++j) {
+      const uint4 rec = rowrec[j];
+      if (rec.z) {
+        if (rec.z == 1u) {
+#pragma unroll
+          for (int i = 0; i < kCols; ++i) H0[i] = H1[i];
+        } else {
+          hrow((int)rec.w, H0);
+        }
+        hrow((int)rec.x, H1);
+      }
+      const unsigned b0 = rec.y & 0xffffu, b1 = rec.y >> 16;
+      unsigned wd[2];
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        unsigned r6[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int i = g * 4 + k * 2;
+          // high halves of the four products of a pixel pair: (b*H) >> 16 for two pixels per PRMT
+          const unsigned P = __byte_perm(b0 * (unsigned)H0[i], b0 * (unsigned)H0[i + 1], 0x7632);
+          const unsigned Q = __byte_perm(b1 * (unsigned)H1[i], b1 * (unsigned)H1[i + 1], 0x7632);
+          // ((P + Q + 2) >> 2) of both halves, left in bytes 1 and 3: ((P + Q) << 6) + (2 << 6)
+          r6[k] = (P + Q) * 64u + 0x00800080u;
+        }
+        wd[g] = (__byte_perm(r6[0], r6[1], 0x7531) & keep[g]) | (bword & ~keep[g]);
+      }
+      uint8_t* d = dst + (long long)(base + j) * tw;
+      if (full) {
+        *reinterpret_cast<uint2*>(d) = make_uint2(wd[0], wd[1]);
+      } else if (count > 0) {  // ragged row end or unaligned rows (T not a multiple of 8)
+#pragma unroll
+        for (int i = 0; i < kCols; ++i)
+          if (i < count) d[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 5) preprocess_u8_kernel(Params p, long long n_rois) {
+  __shared__ __align__(16) uint8_t stage_s[kWarpsPerCta][kStage + 32];  // + misalignment (<= 15) + window over-read (<= 11)
+  __shared__ __align__(16) unsigned hist_s[kWarpsPerCta][4 * 128];  // [sub-histogram][bin pair]: two 16-bit counters per word;
+                                                                   // afterwards the 32 row records of the warp
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // `parts` warps share a ROI (each takes a band of its output rows, and repeats the histogram): small launches would
+  // otherwise leave most of the GPU idle behind the latency of one warp per ROI
+  const int parts = p.slabs;
+  const long long item = (long long)blockIdx.x * kWarpsPerCta + warp;
+  const long long n = item / parts;
+  const int part = (int)(item - n * parts);
+  if (n >= n_rois) return;
+  const int th = p.th, tw = p.tw;
+  const int w = p.w[n], h = p.h[n];
+  const long long start = p.start[n];
+  bool valid = (w >= 1) && (h >= 1) && (w < 65536) && (start >= 0) && (start + (long long)w * h <= p.roi_len);
+  int nh = 0, nw = 0;
+  if (valid) {
+    new_dims(h, w, th, tw, &nh, &nw);
+    valid = (nh >= 1) && (nw >= 1) && (nh <= th) && (nw <= tw);
+  }
+  if (!valid) {
+    if (lane == 0 && part == 0) atomicAdd(p.faults, 1ULL);
+    nh = 0;
+    nw = 0;
+  }
+  const long long total = valid ? (long long)w * h : 0;
+  const uint8_t* src = p.roi + (valid ? start : 0);
+  const int mis = (int)((unsigned long long)src & 15);
+  const bool staged = total > 0 && (mis + total <= kStage + 16);
+  if (valid) {
+    // This kernel resizes what IFCB ROIs almost always are: bilinear (not the identity / exact-2x special cases),
+    // horizontal scale <= 1.6 so that the taps of 4 columns fit an 8-byte window, and small.
+    // Everything else -- ~1 % of ROIs -- is queued for the cluster kernel.
+    const bool fast = (total <= p.big_bytes) && !(nw == w && nh == h) && !(w == 2 * nw && h == 2 * nh) &&
+                      ((long long)w * 10 <= (long long)nw * 16) && (staged || (src + total + 12 <= p.roi + p.roi_len));
+    if (!fast) {
+      if (lane == 0 && part == 0) p.big_list[atomicAdd(p.big_count, 1u)] = (int)n;
+      return;
+    }
+  }
+  uint8_t* out = (uint8_t*)p.out + n * (long long)th * tw;
+  const int top = (th - nh) / 2, left = (tw - nw) / 2;
+  const bool has_border = (nh < th) || (nw < tw);
+  const bool want_mode = (p.border_mode == SPK_BORDER_MODE) && valid && has_border;
+  uint8_t* stage = stage_s[warp];
+  unsigned* hist = hist_s[warp];
+
+  // ---- one pass over the ROI bytes: stage + histogram -------------------------------------------
+  int border = p.border_mode == SPK_BORDER_WHITE ? 255 : 0;
+  if (staged || want_mode) {
+    unsigned tot[8];  // this lane's bins lane*8 .. lane*8+7
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot[k] = 0;
+    unsigned* my = hist + (lane & 3) * 128;
+    auto count_byte = [&](unsigned b) { atomicAdd(&my[b >> 1], 1u << ((b & 1) * 16)); };
+    auto flush = [&]() {
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // word lane*4+k holds bins lane*8+2k, +2k+1
+        unsigned c = 0, d = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const unsigned v = hist[s * 128 + lane * 4 + k];
+          c += v & 0xffffu;
+          d += v >> 16;
+          hist[s * 128 + lane * 4 + k] = 0;
+        }
+        tot[2 * k] += c;
+        tot[2 * k + 1] += d;
+      }
+      __syncwarp();
+    };
+    if (want_mode) {
+      for (int i = lane; i < 4 * 128; i += 32) hist[i] = 0;
+      __syncwarp();
+    }
+    // the aligned 16-byte chunks that cover [src, src + total): chunk c = bytes [c*16 - mis, c*16 - mis + 16) of the ROI
+    const uint4* base = reinterpret_cast<const uint4*>(src - mis);
+    const long long nchunk = (mis + total + 15) >> 4;
+    const uint8_t* buf_lo = p.roi;
+    const uint8_t* buf_hi = p.roi + p.roi_len;
+    long long seg_left = kHistSeg;
+    for (long long c0 = 0; c0 < nchunk; c0 += 32) {
+      const long long c = c0 + lane;
+      if (c < nchunk) {
+        const uint8_t* cp = reinterpret_cast<const uint8_t*>(base + c);
+        const long long lo = c * 16 - mis;  // ROI offset of the chunk's first byte
+        unsigned wds[4];
+        const bool inside = (cp >= buf_lo) && (cp + 16 <= buf_hi);
+        if (inside) {
+          const uint4 q = __ldg(base + c);
+          wds[0] = q.x; wds[1] = q.y; wds[2] = q.z; wds[3] = q.w;
+        } else {  // first / last chunk of the whole .roi buffer: only the bytes that exist
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            unsigned v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint8_t* bp = cp + j * 4 + b;
+              if (bp >= buf_lo && bp < buf_hi) v |= (unsigned)(*bp) << (8 * b);
+            }
+            wds[j] = v;
+          }
+        }
+        if (staged) *reinterpret_cast<uint4*>(stage + c * 16) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        if (want_mode) {
+          if (lo >= 0 && lo + 16 <= total) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              count_byte(wds[j] & 255u);
+              count_byte((wds[j] >> 8) & 255u);
+              count_byte((wds[j] >> 16) & 255u);
+              count_byte(wds[j] >> 24);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const long long o = lo + j;
+              if (o >= 0 && o < total) count_byte((wds[j >> 2] >> (8 * (j & 3))) & 255u);
+            }
+          }
+        }
+      }
+      if (want_mode) {
+        seg_left -= 32 * 16;
+        if (seg_left <= 0) {
+          flush();
+          seg_left = kHistSeg;
+        }
+      }
+    }
+    if (want_mode) {
+      flush();
+      // argmax, lowest bin wins ties: key = count << 8 | (255 - bin)
+      unsigned long long key = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned long long cand = ((unsigned long long)tot[k] << 8) | (unsigned)(255 - (lane * 8 + k));
+        key = cand > key ? cand : key;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+      }
+      border = 255 - (int)(key & 255u);
+    }
+    __syncwarp();
+  }
+
+  // ---- border rows above and below the image (this warp's band of the th output rows) -----------------
+  const int band_lo = (int)((long long)th * part / parts), band_hi = (int)((long long)th * (part + 1) / parts);
+  {
+    const int a0 = band_lo, a1 = min(band_hi, top);            // rows above the image
+    const int b0 = max(band_lo, top + nh), b1 = band_hi;       // rows below
+    if (a1 > a0) warp_fill(out + (long long)a0 * tw, (long long)(a1 - a0) * tw, border, lane);
+    if (b1 > b0) warp_fill(out + (long long)b0 * tw, (long long)(b1 - b0) * tw, border, lane);
+  }
+  const int dy_lo = max(band_lo - top, 0), dy_hi = min(band_hi - top, nh);  // image rows of the band
+  if (dy_hi <= dy_lo) return;
+
+  uint8_t* rows = out + (long long)top * tw;
+  const bool aligned8 = ((tw & 7) == 0) && (((unsigned long long)p.out & 7) == 0);
+  for (int x0 = lane * kCols; x0 < ((tw + 255) & ~255); x0 += 32 * kCols) {
+    if (staged) {
+      SrcView<true> S{(unsigned)__cvta_generic_to_shared(stage + mis), nullptr};
+      image_rows_fast<true>(S, w, h, nw, nh, dy_lo, dy_hi, tw, left, border, x0, rows, aligned8, reinterpret_cast<uint4*>(hist), lane);
+    } else {
+      SrcView<false> S{0u, src};
+      image_rows_fast<false>(S, w, h, nw, nh, dy_lo, dy_hi, tw, left, border, x0, rows, aligned8, reinterpret_cast<uint4*>(hist), lane);
+    }
+  }
+}
+
 __global__ void fill_default_lut(float* lut) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 3 * 256) lut[i] = __fdiv_rn((float)(i & 255), 255.0f);  // ToTensor: true division
@@ -397,13 +793,39 @@ extern "C" int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t ro
   p.out = out;
   p.faults = ctx->d_faults;
   p.slabs = 4;
+  p.big_list = nullptr;
+  p.big_count = nullptr;
+  p.big_bytes = 0;
   const double out_bytes = (double)n * target_h * target_w * channels * (out_dtype == SPK_DTYPE_F32 ? 4 : out_dtype == SPK_DTYPE_BF16 ? 2 : 1);
   // input bytes are data dependent (sum of w*h); the caller adds them -- recorded here: descriptors + output
   ProfScope prof(ctx, SPK_PROF_PREPROCESS, 0.0, out_bytes + 16.0 * n, "preprocess T=%dx%d c=%d dtype=%d n=%lld", target_h, target_w,
                  channels, out_dtype, (long long)n);
   const long long blocks = n * p.slabs;
   if (blocks > 0x7fffffffLL) return fail(ctx, SPK_ERR_UNSUPPORTED, "spk_preprocess: batch too large");
-  preprocess_kernel<<<(unsigned)blocks, kThreads, kHBytes, ctx->stream>>>(p);
+  if (out_dtype == SPK_DTYPE_U8) {
+    if (n > 0x7fffffffLL) return fail(ctx, SPK_ERR_UNSUPPORTED, "spk_preprocess: batch too large");
+    if (ctx->big_cap < n) {
+      if (ctx->d_big_list) cudaFree(ctx->d_big_list);
+      ctx->d_big_list = nullptr;
+      ctx->big_cap = 0;
+      const long long cap = n < 4096 ? 4096 : n + n / 2;
+      SPK_CUDA_OK(ctx, cudaMalloc(&ctx->d_big_list, cap * sizeof(int)));
+      ctx->big_cap = cap;
+    }
+    if (!ctx->d_big_count) SPK_CUDA_OK(ctx, cudaMalloc(&ctx->d_big_count, sizeof(unsigned)));
+    SPK_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_big_count, 0, sizeof(unsigned), ctx->stream));
+    p.big_list = ctx->d_big_list;
+    p.big_count = ctx->d_big_count;
+    p.big_bytes = kBigBytes;
+    p.slabs = n <= 1024 ? 4 : n <= 2048 ? 2 : 1;  // warps per ROI
+    const long long items = n * p.slabs;
+    preprocess_u8_kernel<<<(unsigned)((items + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, (long long)n);
+    SPK_LAUNCH_CHECK(ctx);
+    p.slabs = kBigSlabs;
+    preprocess_big_kernel<<<kBigClusters * kBigSlabs, kThreads, kHBytes, ctx->stream>>>(p);
+  } else {
+    preprocess_kernel<<<(unsigned)blocks, kThreads, kHBytes, ctx->stream>>>(p);
+  }
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;
 }

@@ -37,6 +37,9 @@ struct spk_ctx {
   int64_t launches = 0;
   unsigned long long* d_faults = nullptr;  // device-side count of ROIs with invalid geometry
   float* d_default_lut = nullptr;          // 3*256: v/255 (true fp32 division)
+  int* d_big_list = nullptr;               // K1: queue of heavy-tail ROIs for the cluster kernel
+  unsigned* d_big_count = nullptr;
+  long long big_cap = 0;
   spk::Net* net = nullptr;
   int sm_count = 148;
   bool profiling = false;

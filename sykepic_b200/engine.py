@@ -15,6 +15,7 @@ Reference behaviour mirrored here:
 """
 
 import ctypes as C
+import os
 import re
 from configparser import ConfigParser, NoOptionError
 from pathlib import Path
@@ -94,7 +95,7 @@ class Engine:
     """B200 engine for one model.  `precision`: "fp32" (CUDA-core FFMA convolutions, probabilities
     within 1e-4 of the reference) or "bf16" (tcgen05 tensor-core convolutions, within 2e-2)."""
 
-    def __init__(self, spec, device=0, precision="bf16", max_batch=256, conv_impl="auto", stream=None):
+    def __init__(self, spec, device=0, precision="bf16", max_batch=256, conv_impl="auto", stream=None, pre_chunk=None):
         import torch
 
         if not isinstance(spec, ModelSpec):
@@ -122,7 +123,10 @@ class Engine:
         self._keep = []  # numpy arrays referenced by the library during graph construction
         self._build_graph()
         self.softmax_scale = float(np.float32(np.log(SOFTMAX_EXP)))  # probability.py:192-193
-        self._x = torch.empty((self.max_batch, th, tw), dtype=torch.uint8, device=self.device)
+        # K1 decodes / resizes a whole chunk of a bin per launch (it only reaches HBM speed on thousands of ROIs);
+        # K2 + K3 then walk the chunk in batches.  4096 ROIs = 205 MB of u8 planes at T = 224.
+        self.pre_chunk = max(self.max_batch, int(pre_chunk or os.environ.get("SYKEPIC_PRE_CHUNK", "4096")))
+        self._x = torch.empty((self.pre_chunk, th, tw), dtype=torch.uint8, device=self.device)
         self._thr_dev = None
 
     # ------------------------------------------------------------------ lifecycle
@@ -365,11 +369,14 @@ class Engine:
                        batch_size=None):
         """Decode + transform + network for the `n` ROIs of one bin, everything already on the device."""
         bs = min(batch_size or self.max_batch, self.max_batch)
-        for i in range(0, n, bs):
-            m = min(bs, n - i)
-            self.preprocess(roi_dev, roi_len, start_dev, w_dev, h_dev, m, self._x, offset=i)
-            self.forward(self._x, m, probs_dev[i:i + m], None if label_dev is None else label_dev[i:i + m],
-                         None if cls_dev is None else cls_dev[i:i + m])
+        for c in range(0, n, self.pre_chunk):
+            cm = min(self.pre_chunk, n - c)
+            self.preprocess(roi_dev, roi_len, start_dev, w_dev, h_dev, cm, self._x, offset=c)
+            for i in range(0, cm, bs):
+                m = min(bs, cm - i)
+                lo = c + i
+                self.forward(self._x[i:i + m], m, probs_dev[lo:lo + m], None if label_dev is None else label_dev[lo:lo + m],
+                             None if cls_dev is None else cls_dev[lo:lo + m])
 
     def run_bin(self, adc_text, roi_bytes, batch_size=None, want_labels=False):
         """.adc text + .roi bytes (host) -> (roi_id int32[N], probs float32[N,K][, label, classified]).
