@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
   auto t_empty = [&](int s) { return bar0 + 8u * (4 * kMaxRing + 6 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 8 * (4 * kMaxRing + 8));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMaxRing; ++s) {
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues =====
+    {
       if (BRES) {
         mbar_wait(b_full(0), 0);
         tc_fence_after();
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
       int as = 0, bs = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0;
       int tr = 0;
-      const bool tracing = p.trace != nullptr && blockIdx.x == 5;
+      const bool tracing = p.trace != nullptr && blockIdx.x == 5 && lane == 0;
       for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
         const int m0 = (u / p.tiles_n) * MT;
         const int nvalid = min(MT, p.m_tiles - m0);
@@ -209,11 +210,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols + mt * BN);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // 16 bf16 = 32 bytes along K: +2 in the (addr >> 4) field
-                  tc_mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc, (ch | tap | k) != 0 ? 1u : 0u);
+                  tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc, (ch | tap | k) != 0 ? 1u : 0u);
               }
             }
             if (!BRES) {
-              tc_commit(b_empty(bs));
+              tc_commit_w(b_empty(bs));
               if (++bs == p.nb) {
                 bs = 0;
                 bph ^= 1u;
@@ -222,9 +223,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
           }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
-            if (mt < nvalid) tc_commit(a_empty(slot[mt]));  // frees the halo tile once these MMAs have read it
+            if (mt < nvalid) tc_commit_w(a_empty(slot[mt]));  // frees the halo tile once these MMAs have read it
         }
-        tc_commit(t_full(acc));
+        tc_commit_w(t_full(acc));
         if (++acc == 2) {
           acc = 0;
           accph ^= 1u;

@@ -29,6 +29,7 @@
 
 #include "spk_internal.h"
 #include "tc_common.cuh"
+#include "tc_pair.cuh"
 
 namespace spk {
 namespace {
@@ -58,84 +59,6 @@ struct alignas(64) PairParams {
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
 
-// ---- cluster / cta_group::2 PTX
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-  return r;
-}
-// remote arrive.  CTA-scope release (the default) is enough: what the barrier orders are tcgen05.ld reads of
-// TMEM, which tcgen05.fence::before_thread_sync orders; a .release.cluster arrive was measured at ~1500
-// cycles per call here (it drains the thread's outstanding shared / global stores cluster-wide).
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// wait on a barrier whose arrivals come from both CTAs
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(1000000u)
-        : "memory");
-    if (ok) return;
-    if (it >= 8) {
-      if (t0 == 0) {
-        t0 = clock64();
-      } else if (clock64() - t0 > 4000000000LL) {
-        printf("spk: cluster mbarrier timeout: block %d thread %d barrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
-}
-__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
-      : "memory");
-}
-// D[tmem of both CTAs] (+)= A[smem of both CTAs: 2 x 128 rows] * B[smem of both CTAs: 2 x N/2 rows]^T
-__device__ __forceinline__ void tc2_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive (once the MMAs issued so far have completed) on the barrier at this offset in the CTAs of `mask`
-__device__ __forceinline__ void tc2_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tmem2_alloc(uint32_t slot_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem2_dealloc(uint32_t base, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
-}
-
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_constant__ PairParams p) {
   constexpr int kBHalfBytes = (BN / 2) * kBK * 2;
@@ -161,7 +84,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
   auto t_empty = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 6 + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 8 * (2 * kMaxStages + 8));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -211,8 +135,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
   const int kblocks = p.taps * p.kchunks;
 
   if (warp == 0) {
-    // ===== TMA producer (one thread per CTA) =====
-    if (lane == 0) {
+    // ===== TMA producer (per CTA): whole warp, one elected lane issues =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int u = cluster_id; u < p.units; u += n_clusters) {
@@ -224,9 +148,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * kStageBytes;
           const uint32_t full_leader = mapa_rank(full_bar(stage), 0);
-          if (leader) mbar_expect_tx(full_bar(stage), 2u * kStageBytes);  // both CTAs' bytes land on this barrier
-          tma2_load_4d(sa, &p.map_a[p.tap_map[tap]], full_leader, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-          tma2_load_2d(sa + kABytes, &p.map_b, full_leader, tap * p.cin_pad + c0, nt * BN + (int)rank * (BN / 2));
+          if (leader) mbar_expect_tx_w(full_bar(stage), 2u * kStageBytes);  // both CTAs' bytes land on this barrier
+          tma2_load_4d_w(sa, &p.map_a[p.tap_map[tap]], full_leader, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          tma2_load_2d_w(sa + kABytes, &p.map_b, full_leader, tap * p.cin_pad + c0, nt * BN + (int)rank * (BN / 2));
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -235,8 +159,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread of the leader CTA) =====
-    if (lane == 0 && leader) {
+    // ===== MMA issuer (leader CTA): the whole warp runs the loop with warp-uniform values, one elected lane issues =====
+    if (leader) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, accph = 0;
       for (int u = cluster_id; u < p.units; u += n_clusters) {
@@ -251,14 +175,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
           const uint64_t b_desc = smem_desc_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
-            tc2_mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc, (kb | k) != 0 ? 1u : 0u);
-          tc2_commit_mc(empty_bar(stage), 3);  // frees the stage in both CTAs
+            tc2_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc, (kb | k) != 0 ? 1u : 0u);
+          tc2_commit_mc_w(empty_bar(stage), 3);  // frees the stage in both CTAs
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc2_commit_mc(t_full(acc), 3);  // accumulator complete, both CTAs
+        tc2_commit_mc_w(t_full(acc), 3);  // accumulator complete, both CTAs
         if (++acc == 2) {
           acc = 0;
           accph ^= 1u;

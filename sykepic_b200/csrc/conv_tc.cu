@@ -97,6 +97,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// whole-warp producer variants (see tc_mma_w): all lanes compute the uniform operands, one elected lane issues
+__device__ __forceinline__ void mbar_expect_tx_w(uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_w(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -112,6 +133,26 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Whole-warp variants: every lane executes the (warp-uniform) descriptor arithmetic, so ptxas keeps the operands in
+// uniform registers, and one elected lane issues.  Issuing from inside an `if (lane == 0)` region instead costs
+// ~70 cycles per MMA (SASS: an ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY loop per instruction) -- more than an
+// N <= 128 MMA takes to execute.
+__device__ __forceinline__ void tc_mma_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -165,7 +206,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -195,8 +237,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int kblocks = p.taps * p.kchunks;
 
   if (warp == 0) {
-    // ===== TMA producer (one thread) =====
-    if (lane == 0) {
+    // ===== TMA producer: whole warp, one elected lane issues =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -213,10 +255,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::kStageBytes;
           const bool ds = DS && tap == p.ds_tap;
-          mbar_expect_tx(full_bar(stage), (uint32_t)(kABytes + C::kBBytes * (ds ? 2 : 1)));
-          tma_load_4d(sa, &p.map_a[p.tap_map[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-          tma_load_2d(sa + kABytes, &p.map_b, full_bar(stage), tap * p.cin_pad + c0, nt * BN);
-          if (ds) tma_load_2d(sa + kABytes + C::kBBytes, &p.map_b2, full_bar(stage), c0, nt * BN);
+          mbar_expect_tx_w(full_bar(stage), (uint32_t)(kABytes + C::kBBytes * (ds ? 2 : 1)));
+          tma_load_4d_w(sa, &p.map_a[p.tap_map[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          tma_load_2d_w(sa + kABytes, &p.map_b, full_bar(stage), tap * p.cin_pad + c0, nt * BN);
+          if (ds) tma_load_2d_w(sa + kABytes + C::kBBytes, &p.map_b2, full_bar(stage), c0, nt * BN);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -225,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues =====
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -244,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            tc_mma(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
           if (DS) {
             // the centre tap of a 3x3 / stride 2 / pad 1 filter samples exactly the pixels a 1x1 / stride 2
@@ -255,16 +297,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const uint64_t b2_desc = smem_desc_sw128(sa + kABytes + C::kBBytes);
 #pragma unroll
               for (int k = 0; k < kBK / 16; ++k)
-                tc_mma(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), C::kIdesc, (c | k) != 0 ? 1u : 0u);
+                tc_mma_w(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), C::kIdesc, (c | k) != 0 ? 1u : 0u);
             }
           }
-          tc_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          tc_commit_w(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(tfull_bar(acc));  // accumulator complete
+        tc_commit_w(tfull_bar(acc));  // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;

@@ -39,6 +39,7 @@ struct Op {
   float* d_scale = nullptr;  // bn_relu: scale [C]
   TcConvPlan* tc = nullptr;
   HaloConvPlan* halo = nullptr;
+  HpConvPlan* hpair = nullptr;
   PairConvPlan* pair = nullptr;
   // fused downsample branch (1x1 / stride 2 of the same input, computed by this 3x3 / stride 2 convolution's kernel)
   int ds_out = -1, ds_off = 0, ds_ld = 0;
@@ -79,6 +80,7 @@ static void net_free(Net* net) {
     if (op.d_stem_w) cudaFree(op.d_stem_w);
     if (op.tc) tc_conv_plan_destroy(op.tc);
     if (op.halo) halo_conv_plan_destroy(op.halo);
+    if (op.hpair) hp_conv_plan_destroy(op.hpair);
     if (op.pair) pair_conv_plan_destroy(op.pair);
   }
   if (net->d_head_w) cudaFree(net->d_head_w);
@@ -578,7 +580,11 @@ int spk_net_end(spk_ctx* ctx) {
     if (impl == SPK_CONV_TCGEN05) {
       ConvGeom gm = g;
       gm.n = net->max_batch;
-      if (!taps_only && halo_conv_supported(gm)) {
+      if (!taps_only && hp_conv_supported(gm)) {
+        rc = hp_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.hpair);
+        if (rc) return rc;
+        net->bytes += hp_conv_plan_bytes(op.hpair);
+      } else if (!taps_only && halo_conv_supported(gm)) {
         rc = halo_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.halo);
         if (rc) return rc;
         net->bytes += halo_conv_plan_bytes(op.halo);
@@ -644,9 +650,11 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
                        (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * ((op.res >= 0 ? 2 : 1) + ds_taps) +
                            (double)g.cout * (g.kh * g.kw + ds_taps) * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
                        "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
-                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.halo ? " [halo]" : (op.pair ? " [pair]" : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : "")));
+                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.hpair ? " [halo pair]" : op.halo ? " [halo]" : (op.pair ? " [pair]" : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : "")));
         const void* res = op.res >= 0 ? ptr(op.res, 0) : nullptr;
-        if (op.halo)
+        if (op.hpair)
+          rc = hp_conv_launch(ctx, op.hpair, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
+        else if (op.halo)
           rc = halo_conv_launch(ctx, op.halo, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
         else if (op.pair)
           rc = pair_conv_launch(ctx, op.pair, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));

@@ -143,6 +143,14 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oi
 void pair_conv_plan_destroy(PairConvPlan* p);
 int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y);
 int64_t pair_conv_plan_bytes(const PairConvPlan* p);
+// conv_hp.cu (3x3 / stride 1, Cin and Cout in {64, 128}: halo tiles on CTA pairs, filter bank resident, direct epilogue)
+struct HpConvPlan;
+bool hp_conv_supported(const ConvGeom& g);
+int hp_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
+                        const float* bias, HpConvPlan** out);
+void hp_conv_plan_destroy(HpConvPlan* p);
+int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void* res, void* y);
+int64_t hp_conv_plan_bytes(const HpConvPlan* p);
 // stem.cu: conv 7x7/2 (1 gray plane -> 64) + bias + ReLU + maxpool 3x3/2 fused on tcgen05; u8 in -> bf16 NHWC out
 bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int pool_pad);
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w_folded /*[64][7][7]*/, uint4** d_out);

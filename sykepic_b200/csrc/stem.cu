@@ -123,11 +123,14 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
   auto t_empty = [&](int s) { return base + bar_off + 8u * (kEGroups + kSlots + s); };
   const uint32_t load_bar = base + bar_off + 8u * (kEGroups + 2 * kSlots);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kEGroups + 1 + 2 * kSlots));
+  // every E row is built: the pool buffers (which alias the row buffer the builders read) may be written
+  const uint32_t built_bar = base + bar_off + 8u * (kEGroups + 2 + 2 * kSlots);
   unsigned char* rowbuf = gbase + pool_off;  // bf16 copy of the strip; aliases the pool buffers, which are idle until the first MMA is done
   unsigned char* img = gbase + img_off;
   float* bias_sm = reinterpret_cast<float*>(gbase + bias_off);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
   const int image = blockIdx.x / p.strips;
   const int strip = blockIdx.x - image * p.strips;
   const int p0 = strip * kPoolRowsPerStrip;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
         mbar_init(t_empty(s), kEpiWarps);
       }
       mbar_init(load_bar, 1);
+      mbar_init(built_bar, 4);  // one arrival per builder warp
       mbar_init_fence();
       // weight tile (16 KB, bulk copy) and, when the geometry allows, the u8 strip as ONE TMA box: pixel x of
       // input row y lands at img[(y - y_base) * pitch + x + kXOff]; out-of-image rows / columns are zero-filled
@@ -223,10 +227,11 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(e_ready(yy >> 2));
     }
+    if (lane == 0) mbar_arrive(built_bar);
     if (tid == 0) STEM_TRACE(4);
   } else if (warp == 4) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues =====
+    {
       const uint32_t b_s = base + b_off;
       int groups_seen = 0;
       for (int idx = 0; idx < n_rows; ++idx) {
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
         for (; groups_seen <= (2 * idx + 7) >> 2; ++groups_seen) mbar_wait(e_ready(groups_seen), 0);  // E rows 2idx .. 2idx+7
         mbar_wait(t_empty(slot), (((uint32_t)(idx / kSlots)) & 1u) ^ 1u);
         tc_fence_after();
-        STEM_TRACE(8 + idx);
+        if (lane == 0) STEM_TRACE(8 + idx);
         const uint32_t a_s = base + e_off + (uint32_t)(2 * idx) * kERowBytes;  // E row of filter row 0
         const uint32_t d = tmem_base + (uint32_t)(slot * 64);
         // K = 128: the eight 16-byte K chunks (filter rows) against the hi weights, then again against the lo weights
@@ -242,9 +247,9 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
         for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma(d, smem_desc_interleaved(a_s + 2u * k * kERowBytes, kERowBytes, 128),
+            tc_mma_w(d, smem_desc_interleaved(a_s + 2u * k * kERowBytes, kERowBytes, 128),
                    smem_desc_interleaved(b_s + (uint32_t)pass * kBTile + 2u * k * 1024u, 1024, 128), kIdesc, (pass | k) != 0 ? 1u : 0u);
-        tc_commit(t_full(slot));
+        tc_commit_w(t_full(slot));
       }
     }
   } else {
@@ -278,6 +283,10 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
         for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = fmaxf(acc[qc * 16 + j], __uint_as_float(v[j]));
         if (last_of_window) {
           if (emit) {
+            // The pool buffers alias the bf16 row buffer: wait until the builders have read all of it.  (With the MMA warp
+            // issuing from uniform registers the first pooled row is ready before the builders finish; without this
+            // wait the last conv rows of a strip were built from overwritten pixels.)
+            if (emitted == 0 && qc == 0) mbar_wait(built_bar, 0);
             // + bias, ReLU, bf16; row wo of the pool buffer in 16-byte chunks swizzled by (wo & 7)
             uint32_t o[8];
 #pragma unroll
@@ -413,7 +422,7 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     cache.tw = tw;
   }
   const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes + (size_t)kERows * p.pitch + 32 + 64 * 4 +
-                      8 * (kEGroups + 1 + 2 * kSlots) + 16;
+                      8 * (kEGroups + 3 + 2 * kSlots) + 16;
   SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool want_trace = getenv("SPK_STEM_TRACE") != nullptr;
   static long long* d_trace = nullptr;
