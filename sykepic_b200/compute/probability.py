@@ -127,35 +127,71 @@ def main(
 
     sample_paths = list(sample_paths)
     samples_processed = set()
-    if len(devices) <= 1:
-        net, params = make_params(devices[0])
-        for sample_path in _progress(sample_paths, progress_bar):
-            _guarded(sample_path, net, params, out_dir, force, samples_processed)
-        return samples_processed
+    bar = _progress_bar(len(sample_paths), progress_bar)
 
-    # ---- bins sharded over the GPUs of the box; host-side merge = union of the per-GPU sets
-    shards = shard.assign_bins(sample_paths, len(devices))
-    results = [set() for _ in devices]
-    errors = []
+    def run_on(dev, paths):
+        """One GPU: read -> GPU -> CSV pipeline over its bins (sykepic_b200/pipeline.py)."""
+        from .. import pipeline
 
-    def worker(i):
+        net, params = make_params(dev)
         try:
-            net, params = make_params(devices[i])
-            for sample_path in shards[i]:
-                _guarded(sample_path, net, params, out_dir, force, results[i])
-        except Exception as e:  # engine construction failed: report, do not hang the others
-            errors.append(e)
+            pipe = pipeline.BinPipeline(net, params.classes, out_dir, batch_size=params.batch_size, force=force, suffix=FILE_SUFFIX)
+            return pipe.run(paths, progress=bar)
+        finally:
+            net.close()
 
-    threads = [threading.Thread(target=worker, args=(i,), name=f"spk-gpu{devices[i]}") for i in range(len(devices))]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
-    for r in results:
-        samples_processed |= r
-    return samples_processed
+    try:
+        if len(devices) <= 1:
+            return run_on(devices[0], sample_paths)
+
+        # ---- bins sharded over the GPUs of the box; host-side merge = union of the per-GPU sets (SURVEY 8e)
+        shards = shard.assign_bins(sample_paths, len(devices))
+        results = [set() for _ in devices]
+        errors = []
+
+        def worker(i):
+            try:
+                results[i] = run_on(devices[i], shards[i])
+            except Exception as e:  # engine construction failed: report, do not hang the others
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(i,), name=f"spk-gpu{devices[i]}") for i in range(len(devices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        for r in results:
+            samples_processed |= r
+        return samples_processed
+    finally:
+        if bar is not None:
+            bar.close()
+
+
+class _LockedBar:
+    """tqdm shared by the writer threads of every GPU pipeline."""
+
+    def __init__(self, bar):
+        self.bar, self.lock = bar, threading.Lock()
+
+    def update(self, n):
+        with self.lock:
+            self.bar.update(n)
+
+    def close(self):
+        self.bar.close()
+
+
+def _progress_bar(total, progress_bar):
+    if not progress_bar:
+        return None
+    try:
+        from tqdm import tqdm
+    except ImportError:
+        return None
+    return _LockedBar(tqdm(total=total, desc="Processing samples"))
 
 
 def _progress(items, progress_bar):

@@ -392,29 +392,96 @@ class Engine:
     def run_rois(self, roi_id, w, h, start, roi_np, batch_size=None, want_labels=False):
         """ROI descriptors + the byte stream they index (host numpy) -> probs float32[N,K]
         (or (probs, label int32[N], classified bool[N]))."""
+        return self.submit_rois(w, h, start, roi_np, None, batch_size, want_labels).result()
+
+    def _pinned(self, nbytes):
+        """A pinned host byte buffer of at least `nbytes` from the engine's pool."""
+        pool = self.__dict__.setdefault("_pin_pool", [])
+        for i, t in enumerate(pool):
+            if t.numel() >= nbytes:
+                return pool.pop(i)
+        return self.torch.empty(max(4096, int(nbytes * 1.25)), dtype=self.torch.uint8, pin_memory=True)
+
+    def _unpin(self, t):
+        pool = self.__dict__.setdefault("_pin_pool", [])
+        pool.append(t)
+        pool.sort(key=lambda x: x.numel())
+        del pool[12:]
+
+    def submit_rois(self, w, h, start, roi, roi_len=None, batch_size=None, want_labels=False):
+        """Asynchronous `run_rois`: enqueues H2D, K1, K2 + K3 and the D2H of the results on the engine's stream and
+        returns a handle whose `.result()` waits for them.  `roi`: the .roi byte stream, a numpy array or a (pinned)
+        uint8 torch tensor of which the first `roi_len` bytes are used.  Descriptors go up in one pinned staging copy,
+        results come back into pinned buffers, so nothing on this path blocks the host until `.result()`."""
         torch = self.torch
         n = len(w)
         w = np.ascontiguousarray(w, np.int32)
         h = np.ascontiguousarray(h, np.int32)
         start = np.ascontiguousarray(start, np.int64)
-        roi_np = np.ascontiguousarray(roi_np, np.uint8)
-        validate_rois(w, h, start, roi_np.size, self.th, self.tw)
+        if torch.is_tensor(roi):
+            roi_t = roi
+        else:
+            roi_t = torch.from_numpy(np.ascontiguousarray(roi, np.uint8))
+        if roi_len is None:
+            roi_len = roi_t.numel()
+        validate_rois(w, h, start, roi_len, self.th, self.tw)
         if n == 0:
             probs_h = np.zeros((0, self.k), np.float32)
-            return (probs_h, np.zeros(0, np.int32), np.zeros(0, bool)) if want_labels else probs_h
+            return _Ready((probs_h, np.zeros(0, np.int32), np.zeros(0, bool)) if want_labels else probs_h)
+        k = self.k
+        desc = self._pinned(16 * n)
+        dview = desc.numpy()
+        dview[:8 * n].view(np.int64)[:] = start
+        dview[8 * n:12 * n].view(np.int32)[:] = w
+        dview[12 * n:16 * n].view(np.int32)[:] = h
+        out_bytes = n * k * 4 + (n * 4 + n if want_labels else 0)
+        out = self._pinned(out_bytes)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            roi_dev = torch.from_numpy(roi_np).to(self.device, non_blocking=True)
-            start_dev = torch.from_numpy(start).to(self.device, non_blocking=True)
-            w_dev = torch.from_numpy(w).to(self.device, non_blocking=True)
-            h_dev = torch.from_numpy(h).to(self.device, non_blocking=True)
-            probs = torch.empty((n, self.k), dtype=torch.float32, device=self.device)
-            label = torch.empty(n, dtype=torch.int32, device=self.device) if want_labels else None
-            cls = torch.empty(n, dtype=torch.uint8, device=self.device) if want_labels else None
-            self.run_bin_device(roi_dev, roi_np.size, start_dev, w_dev, h_dev, n, probs, label, cls, batch_size)
-            probs_h = probs.cpu().numpy()
-            if want_labels:
-                return probs_h, label.cpu().numpy(), cls.cpu().numpy().astype(bool)
-        return probs_h
+            roi_dev = roi_t[:max(int(roi_len), 1)].to(self.device, non_blocking=True)
+            desc_dev = desc[:16 * n].to(self.device, non_blocking=True)
+            start_dev = desc_dev[:8 * n].view(torch.int64)
+            w_dev = desc_dev[8 * n:12 * n].view(torch.int32)
+            h_dev = desc_dev[12 * n:16 * n].view(torch.int32)
+            res_dev = torch.empty(out_bytes, dtype=torch.uint8, device=self.device)
+            probs = res_dev[:n * k * 4].view(torch.float32).view(n, k)
+            label = res_dev[n * k * 4:n * k * 4 + n * 4].view(torch.int32) if want_labels else None
+            cls = res_dev[n * k * 4 + n * 4:out_bytes] if want_labels else None
+            self.run_bin_device(roi_dev, int(roi_len), start_dev, w_dev, h_dev, n, probs, label, cls, batch_size)
+            out[:out_bytes].copy_(res_dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return _Pending(self, ev, n, k, want_labels, out, desc, (roi_t, roi_dev, desc_dev, res_dev))
+
+
+class _Ready:
+    def __init__(self, value):
+        self.value = value
+
+    def result(self):
+        return self.value
+
+
+class _Pending:
+    """Results of one `Engine.submit_rois` call, in flight on the engine's stream."""
+
+    def __init__(self, eng, event, n, k, want_labels, out, desc, keep):
+        self.eng, self.event, self.n, self.k, self.want_labels = eng, event, n, k, want_labels
+        self.out, self.desc, self.keep = out, desc, keep
+
+    def result(self):
+        self.event.synchronize()
+        n, k = self.n, self.k
+        raw = self.out.numpy()
+        probs = raw[:n * k * 4].view(np.float32).reshape(n, k).copy()
+        ret = probs
+        if self.want_labels:
+            label = raw[n * k * 4:n * k * 4 + n * 4].view(np.int32).copy()
+            cls = raw[n * k * 4 + n * 4:n * k * 4 + n * 5].astype(bool)
+            ret = (probs, label, cls)
+        self.eng._unpin(self.out)
+        self.eng._unpin(self.desc)
+        self.keep = None
+        return ret
 
 
 # ---------------------------------------------------------------------- host helpers over the C ABI

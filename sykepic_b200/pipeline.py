@@ -1,0 +1,244 @@
+"""Per-GPU host pipeline for `sykepic prob` on raw bins: read -> GPU -> CSV, overlapped.
+
+The reference handles one bin at a time on one thread (sykepic/compute/probability.py:105-115,
+133-162): extract PNGs, run the DataLoader / network, format and write the CSV.  Here the three
+host stages of a bin run on different threads so that the GPU never waits for the disk or for the
+text formatter:
+
+    loader thread(s)   .adc + .roi -> parsed descriptors (C ABI) + the byte stream in a pinned buffer
+    GPU thread         H2D, K1, K2 + K3 per batch, D2H into pinned buffers -- bin i+1 is submitted
+                       before bin i's results are awaited, so the stream always has work queued
+    writer thread(s)   `%.5f` CSV text (C ABI) + file write
+
+Per-bin error policy is the reference's (probability.py:106-114): a bin that raises is logged
+("Faulty raw data" for ValueError, "Unexpected error" otherwise) and skipped, the others go on.
+There is no collective and no cross-bin state: N of these pipelines (one per GPU) run side by side.
+"""
+
+import queue
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+from . import engine as _engine
+from .utils import files, logger
+
+log = logger.get_logger("prob")
+_STOP = object()
+LAST_STATS = []  # stats dict of every finished BinPipeline.run in this process (benchmarks read it)
+
+
+class _PinnedPool:
+    """Reusable pinned host byte buffers (cudaHostAlloc per bin would cost more than the copy)."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.free = []
+        self.lock = threading.Lock()
+
+    def get(self, nbytes):
+        with self.lock:
+            for i, t in enumerate(self.free):
+                if t.numel() >= nbytes:
+                    return self.free.pop(i)
+        cap = max(1 << 20, int(nbytes * 1.25))
+        return self.torch.empty(cap, dtype=self.torch.uint8, pin_memory=True)
+
+    def put(self, t):
+        with self.lock:
+            self.free.append(t)
+            self.free.sort(key=lambda x: x.numel())
+            del self.free[8:]
+
+
+class BinPipeline:
+    """Processes raw bins on one Engine.  `run(sample_paths)` -> set of processed sample names."""
+
+    def __init__(self, net, classes, out_dir, batch_size=None, force=False, suffix=".prob", loaders=2, writers=2, depth=3,
+                 want_labels=False):
+        self.net = net
+        self.classes = list(classes)
+        self.out_dir = out_dir
+        self.batch_size = batch_size
+        self.force = force
+        self.suffix = suffix
+        self.n_loaders = max(1, loaders)
+        self.n_writers = max(1, writers)
+        self.depth = max(1, depth)
+        self.want_labels = want_labels
+        self.stats = {"bins": 0, "rois": 0, "load_s": 0.0, "gpu_wait_s": 0.0, "write_s": 0.0, "roi_bytes": 0, "csv_bytes": 0}
+        self._stat_lock = threading.Lock()
+
+    # ------------------------------------------------------------------ stages
+    def _load(self, sample_path, pool):
+        """-> dict(sample, csv_path, roi_id, w, h, start, buf (pinned tensor), roi_len) or None (skipped)."""
+        sample_path = Path(sample_path)
+        sample = sample_path.name
+        csv_path = files.sample_csv_path(sample_path, self.out_dir, suffix=self.suffix)
+        if csv_path.is_file():
+            if self.force:
+                log.warning(f"{csv_path.name} already exists, overwriting")
+            else:
+                log.warning(f"{csv_path.name} already exists, skipping")
+                return {"sample": sample, "skip": True}
+        t0 = time.perf_counter()
+        with open(sample_path.with_suffix(".adc"), "rb") as fh:
+            adc = fh.read()
+        roi_id, w, h, start = _engine.parse_adc(adc)
+        roi_path = sample_path.with_suffix(".roi")
+        n_bytes = roi_path.stat().st_size
+        buf = pool.get(max(n_bytes, 16))
+        view = buf.numpy()
+        with open(roi_path, "rb") as fh:
+            got = fh.readinto(memoryview(view)[:n_bytes]) if n_bytes else 0
+        if got != n_bytes:
+            pool.put(buf)
+            raise ValueError(f"{roi_path.name}: short read")
+        _engine.validate_rois(w, h, start, n_bytes, self.net.th, self.net.tw)  # FaultyBin / EmptyResize are ValueErrors
+        with self._stat_lock:
+            self.stats["load_s"] += time.perf_counter() - t0
+            self.stats["roi_bytes"] += n_bytes
+        return {"sample": sample, "csv_path": csv_path, "roi_id": roi_id, "w": w, "h": h, "start": start, "buf": buf,
+                "roi_len": n_bytes, "skip": False}
+
+    def _write(self, item):
+        t0 = time.perf_counter()
+        roi_id, probs = item["roi_id"], item["probs"]
+        if len(roi_id) > 1 and np.any(np.diff(roi_id) < 0):  # results sorted by ROI id (probability.py:197)
+            order = np.argsort(roi_id, kind="stable")
+            roi_id, probs = roi_id[order], probs[order]
+        text = _engine.format_prob_csv(self.classes, roi_id, probs)
+        csv_path = Path(item["csv_path"])
+        csv_path.parent.mkdir(parents=True, exist_ok=True)
+        with open(csv_path, "wb") as fh:
+            fh.write(text)
+        with self._stat_lock:
+            self.stats["write_s"] += time.perf_counter() - t0
+            self.stats["csv_bytes"] += len(text)
+            self.stats["bins"] += 1
+            self.stats["rois"] += len(roi_id)
+
+    # ------------------------------------------------------------------ driver
+    def run(self, sample_paths, progress=None):
+        torch = self.net.torch
+        pool = _PinnedPool(torch)
+        sample_paths = list(sample_paths)
+        processed = set()
+        plock = threading.Lock()
+        todo = queue.Queue()
+        for i, sp in enumerate(sample_paths):
+            todo.put((i, sp))
+        loaded = {}  # index -> item | exception marker, consumed in order so that bins finish in submission order
+        loaded_cv = threading.Condition()
+        slots = threading.Semaphore(self.depth + self.n_loaders)  # bounds the pinned memory in flight
+        write_q = queue.Queue(maxsize=self.depth + 2)
+
+        def loader():
+            while True:
+                try:
+                    i, sp = todo.get_nowait()
+                except queue.Empty:
+                    return
+                slots.acquire()
+                try:
+                    item = self._load(sp, pool)
+                except ValueError:
+                    log.exception(f"Faulty raw data for {Path(sp).name}")
+                    item = None
+                except Exception:
+                    log.exception(f"Unexpected error for {Path(sp).name}:")
+                    item = None
+                if item is None or item.get("skip"):
+                    slots.release()
+                with loaded_cv:
+                    loaded[i] = item
+                    loaded_cv.notify_all()
+
+        def writer():
+            while True:
+                item = write_q.get()
+                if item is _STOP:
+                    return
+                try:
+                    self._write(item)
+                    with plock:
+                        processed.add(item["sample"])
+                except Exception:
+                    log.exception(f"Unexpected error for {item['sample']}:")
+                if progress is not None:
+                    progress.update(1)
+
+        loaders = [threading.Thread(target=loader, name=f"spk-load{k}", daemon=True) for k in range(self.n_loaders)]
+        writers = [threading.Thread(target=writer, name=f"spk-write{k}", daemon=True) for k in range(self.n_writers)]
+        for t in loaders + writers:
+            t.start()
+
+        def finish(h):
+            """Await a submitted bin, release its input buffer, hand the results to the writers."""
+            item, handle = h
+            t0 = time.perf_counter()
+            try:
+                out = handle.result()
+            except ValueError:
+                log.exception(f"Faulty raw data for {item['sample']}")
+                out = None
+            except Exception:
+                log.exception(f"Unexpected error for {item['sample']}:")
+                out = None
+            with self._stat_lock:
+                self.stats["gpu_wait_s"] += time.perf_counter() - t0
+            pool.put(item.pop("buf"))
+            slots.release()
+            if out is None:
+                if progress is not None:
+                    progress.update(1)
+                return
+            item["probs"] = out[0] if isinstance(out, tuple) else out
+            if isinstance(out, tuple):
+                item["label"], item["classified"] = out[1], out[2]
+            write_q.put(item)
+
+        pending = None
+        t_run = time.perf_counter()
+        try:
+            for i in range(len(sample_paths)):
+                with loaded_cv:
+                    while i not in loaded:
+                        loaded_cv.wait()
+                    item = loaded.pop(i)
+                if item is None:
+                    if progress is not None:
+                        progress.update(1)
+                    continue
+                if item.get("skip"):  # existing CSV, not forced: counted as processed, like the reference (:141)
+                    with plock:
+                        processed.add(item["sample"])
+                    if progress is not None:
+                        progress.update(1)
+                    continue
+                try:
+                    handle = self.net.submit_rois(item["w"], item["h"], item["start"], item["buf"], item["roi_len"],
+                                                  batch_size=self.batch_size, want_labels=self.want_labels)
+                except Exception:
+                    log.exception(f"Unexpected error for {item['sample']}:")
+                    pool.put(item.pop("buf"))
+                    slots.release()
+                    if progress is not None:
+                        progress.update(1)
+                    continue
+                if pending is not None:
+                    finish(pending)
+                pending = (item, handle)
+            if pending is not None:
+                finish(pending)
+        finally:
+            for _ in writers:
+                write_q.put(_STOP)
+            for t in loaders + writers:
+                t.join()
+            self.stats["run_s"] = time.perf_counter() - t_run
+            LAST_STATS.append(dict(self.stats))
+            del LAST_STATS[:-64]
+        return processed
