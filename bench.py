@@ -359,10 +359,24 @@ def run_b200(args):
         if tc:
             ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12
             peak = float(pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"])
-            roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM convolutions, all launches of a step)",
+            roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions, all launches of a step (conv3x3_hp / conv_pair / conv_tc kernels)",
                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                         "peak_kind": f"{pk_kind} bf16 sustained (cuBLAS)", "traffic": None,
                         "launches_per_step": tc["launches"] // prof_steps, "share_of_step": step_ms["conv_tc"] / total_prof_ms}
+            # the dominant single kernel of the step (largest share): its own achieved rate and, from the committed ncu
+            # capture of the same workload, its DRAM traffic per launch
+            dom = [(ms, fl) for cat, ms, fl, by, what in detail if "[halo pair]" in what and "64->64" in what]
+            tr_file = ROOT / "profiles" / "r1b_traffic.json"
+            if dom and args.arch == "resnet18" and args.batch == 256:
+                d_ms, d_fl = sum(m for m, _ in dom), sum(f for _, f in dom)
+                tr = json.loads(tr_file.read_text()).get("conv3x3_hp_kernel<64>") if tr_file.exists() else None
+                roofline["dominant"] = {"kernel": "conv3x3_hp_kernel<64> (3x3 64->64 @56x56, 4 launches per step)",
+                                        "achieved": d_fl / (d_ms * 1e-3) / 1e12, "frac": d_fl / (d_ms * 1e-3) / 1e12 / peak,
+                                        "ms_per_launch": d_ms / len(dom), "share_of_step": d_ms / prof_steps / total_prof_ms,
+                                        "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                                        "algorithmic_bytes": tr["algorithmic_bytes_per_launch"] if tr else None,
+                                        "traffic_source": tr["source"] if tr else None}
+                roofline["traffic"] = roofline["dominant"]["traffic"]
         else:
             cs = prof.get("conv_simt", {"flops": 0.0, "ms": 1.0, "launches": 0})
             ach = cs["flops"] / (cs["ms"] * 1e-3) / 1e12
