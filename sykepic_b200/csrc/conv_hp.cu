@@ -53,6 +53,8 @@ struct alignas(64) HpParams {
   int a_stage;      // bytes per A stage (multiple of 1024)
   int a_box_bytes;  // (hb + 2) * (w + 2) * 128
   int na;           // A ring depth
+  int reverse;      // walk the units from the last image to the first: the tensors the previous kernel touched last
+                    // are still in L2 (consecutive layers alternate direction)
   long long* trace; // debug (SPK_HP_TRACE=1): clock64 stamps of the leader MMA issuer of cluster 3, else nullptr
 };
 
@@ -127,7 +129,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
 
   // unit -> this CTA's M tile: image and first output row (img == p.n: the odd tile out, TMA zero-fills, nothing stored)
   auto tile_coords = [&](int u, int& img, int& h0) {
-    const int m = 2 * u + (int)rank;
+    const int m = 2 * (p.reverse ? p.units - 1 - u : u) + (int)rank;
     if (m >= p.m_tiles) {
       img = p.n;
       h0 = 0;
@@ -422,6 +424,10 @@ void hp_conv_plan_destroy(HpConvPlan* p) {
 }
 
 int64_t hp_conv_plan_bytes(const HpConvPlan* p) { return p ? p->bytes : 0; }
+
+void hp_conv_plan_set_reverse(HpConvPlan* p, int reverse) {
+  if (p) p->prm.reverse = reverse ? 1 : 0;
+}
 
 int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void* res, void* y) {
   if (n <= 0) return SPK_OK;

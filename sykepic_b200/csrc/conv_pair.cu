@@ -55,6 +55,7 @@ struct alignas(64) PairParams {
   int m_tiles, units;
   int taps, kchunks, cin_pad;
   int stages, res_slots;
+  int reverse;  // walk the units last-to-first (consecutive layers alternate direction: the previous kernel's last tiles are in L2)
   long long* trace;  // debug (SPK_PAIR_TRACE=1): clock64 stamps of one CTA's epilogue thread 0
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
@@ -116,6 +117,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
 
   // unit -> this CTA's M tile (box origin) and the N tile
   auto decode = [&](int u, int& nt, int& w0, int& h0, int& n0) {
+    if (p.reverse) u = p.units - 1 - u;
     nt = u % p.tiles_n;
     int m = (u / p.tiles_n) * 2 + (int)rank;
     if (m >= p.m_tiles) {  // the odd tile out: a box past the batch -- TMA zero-fills the loads and clips the store
@@ -458,6 +460,10 @@ void pair_conv_plan_destroy(PairConvPlan* p) {
 }
 
 int64_t pair_conv_plan_bytes(const PairConvPlan* p) { return p ? p->bytes : 0; }
+
+void pair_conv_plan_set_reverse(PairConvPlan* p, int reverse) {
+  if (p) p->prm.reverse = reverse ? 1 : 0;
+}
 
 int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y) {
   if (n <= 0) return SPK_OK;

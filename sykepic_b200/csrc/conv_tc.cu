@@ -53,6 +53,7 @@ struct alignas(64) TcParams {
   int tiles_w, tiles_h, tiles_img, tiles_n;
   int taps, kchunks, cin_pad;
   int total_tiles;
+  int reverse;  // walk the tiles last-to-first (see conv_hp.cu)
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
 
@@ -242,8 +243,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n;
-        int m = tile / p.tiles_n;
+        const int tl = p.reverse ? p.total_tiles - 1 - tile : tile;
+        const int nt = tl % p.tiles_n;
+        int m = tl / p.tiles_n;
         const int twi = m % p.tiles_w;
         m /= p.tiles_w;
         const int thi = m % p.tiles_h;
@@ -323,8 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.tiles_n;
-      int m = tile / p.tiles_n;
+      const int tl = p.reverse ? p.total_tiles - 1 - tile : tile;
+      const int nt = tl % p.tiles_n;
+      int m = tl / p.tiles_n;
       const int twi = m % p.tiles_w;
       m /= p.tiles_w;
       const int thi = m % p.tiles_h;
@@ -633,6 +636,10 @@ void tc_conv_plan_destroy(TcConvPlan* p) {
 }
 
 int64_t tc_conv_plan_bytes(const TcConvPlan* p) { return p ? p->bytes : 0; }
+
+void tc_conv_plan_set_reverse(TcConvPlan* p, int reverse) {
+  if (p) p->prm.reverse = reverse ? 1 : 0;
+}
 
 template <int BN, bool DS = false>
 static int launch_bn(spk_ctx* ctx, const TcParams& prm) {

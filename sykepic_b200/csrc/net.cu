@@ -616,6 +616,22 @@ int spk_net_end(spk_ctx* ctx) {
     std::vector<float>().swap(op.w_host);
     std::vector<float>().swap(op.b_host);
   }
+  // ---- L2-friendly traversal: launch k walks its tiles in the direction opposite to launch k-1 (the stem goes forward)
+  if (!getenv("SPK_NO_ZIGZAG")) {
+    int dir = 0;
+    for (auto& op : net->ops) {
+      if (op.kind == kOpNop) continue;
+      if (op.kind == kOpConv && op.impl == SPK_CONV_TCGEN05) {
+        dir ^= 1;
+        if (op.hpair) hp_conv_plan_set_reverse(op.hpair, dir);
+        else if (op.pair) pair_conv_plan_set_reverse(op.pair, dir);
+        else if (op.tc) tc_conv_plan_set_reverse(op.tc, dir);
+        else dir = 0;  // single-CTA halo kernel: forward only
+      } else {
+        dir = 0;  // every other kernel walks forward
+      }
+    }
+  }
   net->ended = true;
   return SPK_OK;
 }

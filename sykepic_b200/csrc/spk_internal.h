@@ -127,6 +127,8 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y, void* y_ds = nullptr);
 int64_t tc_conv_plan_bytes(const TcConvPlan* p);
+// consecutive layers walk their tiles in alternating directions, so that a kernel starts on what the previous one left in L2
+void tc_conv_plan_set_reverse(TcConvPlan* p, int reverse);
 // conv_halo.cu (3x3 / stride 1: halo tile resident in shared memory, taps = shifted descriptors, TMA-store epilogue)
 struct HaloConvPlan;
 bool halo_conv_supported(const ConvGeom& g);
@@ -143,6 +145,7 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oi
 void pair_conv_plan_destroy(PairConvPlan* p);
 int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y);
 int64_t pair_conv_plan_bytes(const PairConvPlan* p);
+void pair_conv_plan_set_reverse(PairConvPlan* p, int reverse);
 // conv_hp.cu (3x3 / stride 1, Cin and Cout in {64, 128}: halo tiles on CTA pairs, filter bank resident, direct epilogue)
 struct HpConvPlan;
 bool hp_conv_supported(const ConvGeom& g);
@@ -151,6 +154,7 @@ int hp_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw
 void hp_conv_plan_destroy(HpConvPlan* p);
 int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void* res, void* y);
 int64_t hp_conv_plan_bytes(const HpConvPlan* p);
+void hp_conv_plan_set_reverse(HpConvPlan* p, int reverse);
 // stem.cu: conv 7x7/2 (1 gray plane -> 64) + bias + ReLU + maxpool 3x3/2 fused on tcgen05; u8 in -> bf16 NHWC out
 bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int pool_pad);
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w_folded /*[64][7][7]*/, uint4** d_out);
