@@ -305,16 +305,22 @@ def run_b200(args):
     host_in = [(w, h, start, torch.from_numpy(roi).pin_memory().numpy()) for w, h, start, roi in chunks]
     ids = np.arange(chunk, dtype=np.int32)
 
-    def call_host(i):
+    def submit_host(i):
         w, h, start, roi = host_in[i % n_pool]
-        eng.run_rois(ids, w, h, start, roi, want_labels=True)
+        return eng.submit_rois(w, h, start, roi, want_labels=True)
 
-    call_host(0)
+    submit_host(0).result()
     barrier()
-    e2e_calls = max(1, -(-args.steps // G))
+    e2e_calls = max(2, -(-args.steps // G))
     t0 = time.perf_counter()
+    # the host API as `probability.main` drives it (pipeline.BinPipeline): bin i+1 is submitted before bin i is awaited
+    pending = None
     for i in range(e2e_calls):
-        call_host(i)
+        nxt = submit_host(i)
+        if pending is not None:
+            pending.result()
+        pending = nxt
+    pending.result()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -405,7 +411,7 @@ def run_b200(args):
                        "k1_chunk": f"K1 decodes {chunk} ROIs ({G} batches) per launch, every {G}th step; K2+K3 per batch",
                        "conv_gflop_per_roi_logical": CONV_GFLOP.get(args.arch) if args.target == 224 else None},
             "e2e": {"value": args.gpus * args.batch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": f"Engine.run_rois on bins of {chunk} ROIs (host pinned in, host numpy out), {e2e_calls} calls"},
+                    "d2h_bytes_per_step": d2h, "api": f"Engine.submit_rois(...).result() on bins of {chunk} ROIs, one bin in flight ahead (as probability.main / BinPipeline does): pinned host in, host numpy out, {e2e_calls} calls"},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": roofline,

@@ -166,24 +166,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (leader CTA): the whole warp runs the loop with warp-uniform values, one elected lane issues =====
+    // ===== MMA issuer (leader CTA): the whole warp runs the loop with warp-uniform values, one elected lane issues.
+    // A satisfied mbarrier wait + tcgen05 fence still costs ~150-200 cycles of this warp (trace: 385 cycles per
+    // 1150-cycle unit at N = 64), during which the MMA queue runs dry.  The waits for the NEXT chunk (its halo stage,
+    // and the accumulator buffer when it starts a unit) are therefore done after the FIFTH tap of the current chunk,
+    // while four taps' worth of MMAs are still queued. =====
     if (leader) {
       mbar_wait(b_full, 0);
-      tc_fence_after();
       int as = 0, acc = 0, tr = 0;
       uint32_t aph = 0, accph = 0;
       const bool tracing = p.trace != nullptr && cluster_id == 3 && lane == 0;
-      for (int u = cluster_id; u < p.units; u += n_clusters) {
-        if (tracing && tr < 250) p.trace[tr++] = clock64();
-        mbar_wait_cluster(t_empty(acc), accph ^ 1u);  // both CTAs have drained this accumulator buffer
+      // flat sequence of chunks: chunk c of unit u; `ready` = the barriers of the chunk about to be issued have been waited for
+      auto wait_chunk = [&](int ch, int as_, uint32_t aph_, int acc_, uint32_t accph_) {
+        if (ch == 0) mbar_wait_cluster(t_empty(acc_), accph_ ^ 1u);  // both CTAs have drained this accumulator buffer
+        mbar_wait(a_full(as_), aph_);
         tc_fence_after();
+      };
+      if (cluster_id < p.units) wait_chunk(0, as, aph, acc, accph);
+      for (int u = cluster_id; u < p.units; u += n_clusters) {
         if (tracing && tr < 250) p.trace[tr++] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int ch = 0; ch < p.kchunks; ++ch) {
-          mbar_wait(a_full(as), aph);
-          tc_fence_after();
-          if (tracing && tr < 250) p.trace[tr++] = clock64();
           const uint32_t sa = a_s + (uint32_t)as * p.a_stage;
+          // what comes after this chunk
+          int as_n = as + 1;
+          uint32_t aph_n = aph;
+          if (as_n == p.na) {
+            as_n = 0;
+            aph_n ^= 1u;
+          }
+          const bool last_ch = ch + 1 == p.kchunks;
+          const bool has_next = !last_ch || (u + n_clusters < p.units);
+          int acc_n = acc;
+          uint32_t accph_n = accph;
+          if (last_ch && ++acc_n == 2) {
+            acc_n = 0;
+            accph_n ^= 1u;
+          }
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int r = tap / 3, s = tap - 3 * r;
@@ -193,12 +212,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // 16 bf16 = 32 bytes along K: +2 in the (addr >> 4) field
               tc2_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc, (ch | tap | k) != 0 ? 1u : 0u);
+            if (tap == 4 && has_next) wait_chunk(last_ch ? 0 : ch + 1, as_n, aph_n, acc_n, accph_n);
           }
           tc2_commit_mc_w(a_empty(as), 3);  // frees the halo stage in both CTAs once these MMAs have read it
-          if (++as == p.na) {
-            as = 0;
-            aph ^= 1u;
-          }
+          as = as_n;
+          aph = aph_n;
         }
         tc2_commit_mc_w(t_full(acc), 3);  // accumulator complete, both CTAs
         if (++acc == 2) {

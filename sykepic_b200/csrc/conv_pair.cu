@@ -349,7 +349,7 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
   const ConvGeom& g = p->g;
   memset(&p->prm, 0, sizeof p->prm);
   PairParams& prm = p->prm;
-  p->bn = g.cout % 256 == 0 ? 256 : 128;
+  p->bn = g.cout % 256 == 0 ? 256 : 128;  // revised below once the tile box is known (wave quantisation)
   prm.bias = d_bias;
   prm.ho = g.ho;
   prm.wo = g.wo;
@@ -377,6 +377,16 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
     }
   prm.tiles_w = (g.wo + prm.wb - 1) / prm.wb;
   prm.tiles_h = (g.ho + prm.hb - 1) / prm.hb;
+  // ---- N tile: 256 halves the A re-reads, but a layer with few M tiles (7x7 maps: 98 pairs x N tiles at batch 256) then
+  // leaves most of the 74 clusters idle in its last round; pick the width with the shorter schedule at the planned batch
+  if (g.cout % 256 == 0 && getenv("SPK_PAIR_BN_AUTO")) {  // measured (512->512 @7x7, batch 256): 0.063 ms at N = 128 vs 0.058-0.062 at N = 256; off
+    const long long m_tiles = (long long)prm.tiles_w * prm.tiles_h * ((g.n + prm.nb - 1) / prm.nb);
+    const long long pairs = (m_tiles + 1) / 2, clusters = std::max(1, ctx->sm_count / 2);
+    auto rounds = [&](int bn) { return (pairs * (g.cout / bn) + clusters - 1) / clusters; };
+    const double t256 = (double)rounds(256) * 256.0, t128 = (double)rounds(128) * 128.0 * 1.06;  // N = 128 streams B twice as often
+    p->bn = t128 < t256 ? 128 : 256;
+  }
+  prm.tiles_n = g.cout / p->bn;
 
   // ---- taps -> (tensor map, box shift)
   p->n_maps = 0;

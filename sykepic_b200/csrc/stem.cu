@@ -263,51 +263,55 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = -INFINITY;
     int emitted = 0;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
     for (int idx = 0; idx < n_rows; ++idx) {
       const int i = c_lo + idx, slot = idx % kSlots;
       __syncwarp();  // tcgen05.ld below is warp-collective
       mbar_wait(t_full(slot), ((uint32_t)(idx / kSlots)) & 1u);
       tc_fence_after();
       if (tid == 160) STEM_TRACE(24 + idx);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64 + half * 32);
       const bool last_of_window = (i & 1) || (i == p.hc - 1);
       const int prow = i >> 1;
       const bool emit = last_of_window && prow >= p0 && prow <= p1;
       unsigned char* pool = gbase + pool_off + (emitted & 1) * kPoolBytes;
+      // The pool buffers alias the bf16 row buffer: wait until the builders have read all of it.  (With the MMA warp
+      // issuing from uniform registers the first pooled row is ready before the builders finish; without this wait
+      // the last conv rows of a strip were built from overwritten pixels.)
+      if (emit && emitted == 0) mbar_wait(built_bar, 0);
 #pragma unroll
-      for (int qc = 0; qc < 2; ++qc) {
+      for (int qc = 0; qc < 2; ++qc) {  // 16 channels at a time: acc[32] + v[32] would not fit the 72-register budget
         uint32_t v[16];
-        tmem_ld16(taddr + qc * 16, v);
+        tmem_ld16(taddr0 + (uint32_t)(slot * 64 + qc * 16), v);
         tmem_ld_wait();
+        if (qc == 1) {  // the accumulator slot is free as soon as it has been read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty(slot));
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = fmaxf(acc[qc * 16 + j], __uint_as_float(v[j]));
-        if (last_of_window) {
-          if (emit) {
-            // The pool buffers alias the bf16 row buffer: wait until the builders have read all of it.  (With the MMA warp
-            // issuing from uniform registers the first pooled row is ready before the builders finish; without this
-            // wait the last conv rows of a strip were built from overwritten pixels.)
-            if (emitted == 0 && qc == 0) mbar_wait(built_bar, 0);
-            // + bias, ReLU, bf16; row wo of the pool buffer in 16-byte chunks swizzled by (wo & 7)
-            uint32_t o[8];
+        if (emit) {
+          // + bias, ReLU, bf16; row wo of the pool buffer in 16-byte chunks swizzled by (wo & 7)
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + half * 32 + qc * 16 + j);
-              __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(acc[qc * 16 + j] + b2.x, 0.f), fmaxf(acc[qc * 16 + j + 1] + b2.y, 0.f));
-              o[j >> 1] = *reinterpret_cast<uint32_t*>(&t);
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = qc * 16 + c * 8 + 2 * j;
+              const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + half * 32 + e);
+              __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(acc[e] + b2.x, 0.f), fmaxf(acc[e + 1] + b2.y, 0.f));
+              o[j] = *reinterpret_cast<uint32_t*>(&t);
             }
-            const int c0 = 4 * half + 2 * qc;
-            *reinterpret_cast<uint4*>(pool + wo * 128 + ((c0 ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(pool + wo * 128 + (((c0 + 1) ^ (wo & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            *reinterpret_cast<uint4*>(pool + wo * 128 + (((4 * half + 2 * qc + c) ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it
+        }
+        if (last_of_window) {
+          // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it (an even last row
+          // ends the image, what it leaves in acc is never used)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = (i & 1) ? __uint_as_float(v[j]) : -INFINITY;
+          for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = __uint_as_float(v[j]);
         }
       }
-      // the accumulator slot is free as soon as it has been read
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty(slot));
       if (tid == 160 && idx == 2) STEM_TRACE(56);
       if (tid == 415 && idx == 2) STEM_TRACE(59);
       if (emit) {
