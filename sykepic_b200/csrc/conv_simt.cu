@@ -241,6 +241,44 @@ __global__ void affine_relu_kernel(long long pixels, int c, int ldx, const float
   }
 }
 
+// bf16, c % 8 == 0, ldx % 8 == 0: 8 channels (16 bytes) per thread and iteration; the scale / shift vectors sit in
+// shared memory.  (The scalar kernel above ran at 1.6 TB/s on DenseNet-121's pre-activations: 13.4 of 21 ms per step.)
+__global__ void __launch_bounds__(256) affine_relu_bf16x8_kernel(unsigned pixels, int c, int ldx, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, const __nv_bfloat16* __restrict__ x,
+                                                                  __nv_bfloat16* __restrict__ y, int relu) {
+  extern __shared__ float ss[];  // [scale c][shift c]
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    ss[i] = __ldg(scale + i);
+    ss[c + i] = __ldg(shift + i);
+  }
+  __syncthreads();
+  const unsigned groups = (unsigned)c >> 3;
+  const unsigned long long total = (unsigned long long)pixels * groups;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned p = (unsigned)(i / groups), g = (unsigned)(i - (unsigned long long)p * groups);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (size_t)p * ldx + g * 8));
+    const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const float4 s0 = *reinterpret_cast<const float4*>(ss + g * 8), s1 = *reinterpret_cast<const float4*>(ss + g * 8 + 4);
+    const float4 h0 = *reinterpret_cast<const float4*>(ss + c + g * 8), h1 = *reinterpret_cast<const float4*>(ss + c + g * 8 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(b2[j]);
+      float a = fmaf(f.x, sc[2 * j], sh[2 * j]), b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+      if (relu) {
+        a = fmaxf(a, 0.f);
+        b = fmaxf(b, 0.f);
+      }
+      const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+      ow[j] = *reinterpret_cast<const uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(y + (size_t)p * c + g * 8) = o;
+  }
+}
+
 template <typename TIn, typename TOut>
 int launch_typed(spk_ctx* ctx, const ConvArgs& a) {
   const ConvGeom& g = a.g;
@@ -285,6 +323,10 @@ int launch_affine_relu(spk_ctx* ctx, long long pixels, int c, int ldx, const flo
   const unsigned blocks = grid_for(ctx, total, 256);
   if (dtype == SPK_DTYPE_F32)
     affine_relu_kernel<float><<<blocks, 256, 0, ctx->stream>>>(pixels, c, ldx, scale, shift, (const float*)x, (float*)y, relu);
+  else if (dtype == SPK_DTYPE_BF16 && (c & 7) == 0 && (ldx & 7) == 0 && pixels < 0xffffffffLL && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 &&
+           c <= 4096)
+    affine_relu_bf16x8_kernel<<<grid_for(ctx, total / 8, 256), 256, 2 * c * sizeof(float), ctx->stream>>>(
+        (unsigned)pixels, c, ldx, scale, shift, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, relu);
   else if (dtype == SPK_DTYPE_BF16)
     affine_relu_kernel<__nv_bfloat16><<<blocks, 256, 0, ctx->stream>>>(pixels, c, ldx, scale, shift,
                                                                         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, relu);

@@ -169,3 +169,32 @@ def test_cli_prob_then_class(model_dirs, tmp_path):
     assert cli(["class", str(out), "-t", str(thr), "-o", str(tmp_path / "class.csv")]) == 0
     lines = (tmp_path / "class.csv").read_text().splitlines()
     assert lines[0].startswith("Time,") and len(lines) == 4
+
+
+def test_densenet121_matches_oracle(tmp_path):
+    """BASELINE config 4.  The reference raises for DenseNet at these sizes, so there is no golden
+    from it: the defined behaviour (torchvision's forward + the syke-pic head) is checked against the oracle's
+    torch-CPU fp32 restatement of it, in FP32 (1e-4) and BF16 (spread-aware 2e-2 gate)."""
+    from oracle import ifcb as o_ifcb
+    from oracle import pipeline
+
+    mdir = synth.write_model_dir(tmp_path / "model_d121", arch="densenet121", t=224, head=(256, 128), seed=3, border="mode",
+                                 imagenet_normalization=False, randomize_bn=True, logit_gain=8.0)
+    model = pipeline.prepare_model(mdir)
+    b = synth.synth_bin(1011, 20)
+    rows = o_ifcb.parse_adc_text(b["adc_text"])
+    want = pipeline.net_pass(model, rows, np.asarray(b["roi_bytes"], np.uint8), batch_size=32)
+    wp = np.array([p for _, p in want], np.float32)
+    for precision in ("fp32", "bf16"):
+        eng = engine.Engine(mdir, precision=precision, max_batch=32)
+        try:
+            rid, probs = eng.run_bin(b["adc_text"], b["roi_bytes"])
+            assert rid.tolist() == [r for r, _ in want]
+            err = np.abs(probs - wp).max(axis=1)
+            if precision == "fp32":
+                assert err.max() <= FP32_PROB_TOL, float(err.max())
+            else:
+                logits = np.log(np.maximum(wp, 1e-30)) / np.log(engine.SOFTMAX_EXP)  # up to a per-ROI constant
+                assert (err <= _bf16_tol(logits)).all(), float(err.max())
+        finally:
+            eng.close()
