@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--chunk-batches", type=int, default=16,
                     help="batches per bin chunk: K1 decodes a chunk per launch (as Engine.run_bin_device does), K2+K3 run per batch")
     ap.add_argument("--target", type=int, default=224)
-    ap.add_argument("--precision", choices=("bf16", "fp32"), default="bf16")
+    ap.add_argument("--precision", choices=("bf16", "fp32", "fp32_tc"), default="bf16")
     ap.add_argument("--conv-impl", choices=("auto", "simt", "tcgen05", "taps"), default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-detail", metavar="FILE", help="write the per-launch timing table of the roofline pass")

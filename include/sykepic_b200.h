@@ -47,9 +47,12 @@ extern "C" {
 
 /* ---- enums -------------------------------------------------------------------------- */
 enum { SPK_BORDER_MODE = 0, SPK_BORDER_BLACK = 1, SPK_BORDER_WHITE = 2 }; /* sykepic/train/image.py:20-28 */
-enum { SPK_DTYPE_F32 = 0, SPK_DTYPE_BF16 = 1, SPK_DTYPE_U8 = 2 };
+enum { SPK_DTYPE_F32 = 0, SPK_DTYPE_BF16 = 1, SPK_DTYPE_U8 = 2,
+       SPK_DTYPE_SPLIT = 3 /* internal activation format of the FP32 precision: bf16 hi | bf16 lo in one 32-bit word */ };
 enum { SPK_LAYOUT_NCHW = 0, SPK_LAYOUT_NHWC = 1 };
-enum { SPK_PRECISION_FP32 = 0, SPK_PRECISION_BF16 = 1 };
+enum { SPK_PRECISION_FP32 = 0, SPK_PRECISION_BF16 = 1,
+       SPK_PRECISION_FP32_TC = 2 /* fp32-level accuracy on the bf16 tensor cores (activations and weights as bf16 hi + lo;
+                                    ~1e-5 relative per layer from the tensor core's truncating fp32 accumulation) */ };
 /* implementation selector for convolutions in bf16 precision: AUTO / TCGEN05 pick the halo-resident
  * kernel for 3x3 stride-1 layers on large maps and the tap-per-TMA kernel elsewhere; TCGEN05_TAPS
  * forces the tap-per-TMA kernel everywhere (A/B comparison). */

@@ -1,7 +1,7 @@
 """`sykepic` command line: the `prob` and `class` sub-commands of the reference
 (sykepic/__main__.py:63-99 and :134-190) with identical flags, served by the B200 path.
 
-Extra flags of `prob` (not in the reference): `--precision {fp32,bf16}` and `--gpus N`.
+Extra flags of `prob` (not in the reference): `--precision {fp32,fp32_tc,bf16}` and `--gpus N`.
 The reference's other sub-commands (train, feat, size, abundance, class_stats,
 features_per_prediction) are outside this build.
 """
@@ -30,7 +30,7 @@ def build_parser():
     prob_parser.add_argument("-w", "--num-workers", type=int, default=2, metavar="INT",
                              help="Accepted for compatibility (no loader processes on this path)")
     prob_parser.add_argument("-f", "--force", action="store_true", help="Force overwrite of previous probabilities")
-    prob_parser.add_argument("--precision", choices=("fp32", "bf16"), default=None,
+    prob_parser.add_argument("--precision", choices=("fp32", "fp32_tc", "bf16"), default=None,
                              help="fp32 (default; within 1e-4 of the reference) or bf16 tensor cores (within 2e-2)")
     prob_parser.add_argument("--gpus", dest="devices", type=int, default=None, metavar="N",
                              help="Shard bins over the first N GPUs of this box (default 1)")

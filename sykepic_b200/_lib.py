@@ -21,9 +21,9 @@ SPK_ERR_UNSUPPORTED = -7
 SPK_ERR_STATE = -8
 
 BORDER = {"mode": 0, "black": 1, "white": 2}
-DTYPE_F32, DTYPE_BF16, DTYPE_U8 = 0, 1, 2
+DTYPE_F32, DTYPE_BF16, DTYPE_U8, DTYPE_SPLIT = 0, 1, 2, 3
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+PRECISION_FP32, PRECISION_BF16, PRECISION_FP32_TC = 0, 1, 2
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05, CONV_TCGEN05_TAPS = 0, 1, 2, 3
 INT32_MAX = 2**31 - 1
 PROF_CATEGORIES = ["preprocess", "conv_tc", "conv_simt", "stem", "pool", "bn_relu", "head", "other"]

@@ -8,6 +8,8 @@
 //
 // GEMM view: M = N*Ho*Wo output pixels, N = Cout, K = kh*kw*Cin ordered (r, s, c).
 // CTA tile 128 x 64 x 16, 256 threads, 8x4 accumulators per thread.
+#include <type_traits>
+
 #include "spk_internal.h"
 
 namespace spk {
@@ -21,6 +23,8 @@ template <>
 __device__ __forceinline__ float ld_act<float>(const float* p) { return __ldg(p); }
 template <>
 __device__ __forceinline__ float ld_act<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float ld_act<SplitF>(const SplitF* p) { return split_load(__ldg(&p->v)); }
 
 template <typename T>
 __device__ __forceinline__ void st_act(T* p, float v);
@@ -28,6 +32,8 @@ template <>
 __device__ __forceinline__ void st_act<float>(float* p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void st_act<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ void st_act<SplitF>(SplitF* p, float v) { p->v = split_store(v); }
 
 struct ConvArgs {
   ConvGeom g;
@@ -92,7 +98,12 @@ __global__ void __launch_bounds__(THREADS) conv_simt_kernel(ConvArgs a) {
         const int hi = hi0 + r, wi = wi0 + s;
         if (hi >= 0 && hi < g.h && wi >= 0 && wi < g.w) {
           const TIn* p = x + (((long long)img * g.h + hi) * g.w + wi) * g.ldx + c0;
-          if constexpr (sizeof(TIn) == 4) {
+          if constexpr (std::is_same<TIn, SplitF>::value) {
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(p));
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+            av[0] = split_load(q0.x); av[1] = split_load(q0.y); av[2] = split_load(q0.z); av[3] = split_load(q0.w);
+            av[4] = split_load(q1.x); av[5] = split_load(q1.y); av[6] = split_load(q1.z); av[7] = split_load(q1.w);
+          } else if constexpr (sizeof(TIn) == 4) {
             const float4 q0 = __ldg(reinterpret_cast<const float4*>(p));
             const float4 q1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
             av[0] = q0.x; av[1] = q0.y; av[2] = q0.z; av[3] = q0.w;
@@ -310,6 +321,8 @@ int launch_avgpool(spk_ctx* ctx, int n, int h, int w, int c, int ldx, int k, int
   else if (dtype == SPK_DTYPE_BF16)
     avgpool_kernel<__nv_bfloat16><<<blocks, 256, 0, ctx->stream>>>(n, h, w, c, ldx, k, stride, ho, wo, ldy,
                                                                     (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
+  else if (dtype == SPK_DTYPE_SPLIT)
+    avgpool_kernel<SplitF><<<blocks, 256, 0, ctx->stream>>>(n, h, w, c, ldx, k, stride, ho, wo, ldy, (const SplitF*)x, (SplitF*)y);
   else
     return fail(ctx, SPK_ERR_UNSUPPORTED, "avgpool: dtype %d", dtype);
   SPK_LAUNCH_CHECK(ctx);
@@ -330,6 +343,8 @@ int launch_affine_relu(spk_ctx* ctx, long long pixels, int c, int ldx, const flo
   else if (dtype == SPK_DTYPE_BF16)
     affine_relu_kernel<__nv_bfloat16><<<blocks, 256, 0, ctx->stream>>>(pixels, c, ldx, scale, shift,
                                                                         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, relu);
+  else if (dtype == SPK_DTYPE_SPLIT)
+    affine_relu_kernel<SplitF><<<blocks, 256, 0, ctx->stream>>>(pixels, c, ldx, scale, shift, (const SplitF*)x, (SplitF*)y, relu);
   else
     return fail(ctx, SPK_ERR_UNSUPPORTED, "affine_relu: dtype %d", dtype);
   SPK_LAUNCH_CHECK(ctx);
@@ -353,6 +368,8 @@ int launch_conv_simt(spk_ctx* ctx, const ConvGeom& g, const void* x, int x_dtype
   if (x_dtype == SPK_DTYPE_BF16 && y_dtype == SPK_DTYPE_BF16) return launch_typed<__nv_bfloat16, __nv_bfloat16>(ctx, a);
   if (x_dtype == SPK_DTYPE_U8 && y_dtype == SPK_DTYPE_F32) return launch_typed<uint8_t, float>(ctx, a);
   if (x_dtype == SPK_DTYPE_U8 && y_dtype == SPK_DTYPE_BF16) return launch_typed<uint8_t, __nv_bfloat16>(ctx, a);
+  if (x_dtype == SPK_DTYPE_SPLIT && y_dtype == SPK_DTYPE_SPLIT) return launch_typed<SplitF, SplitF>(ctx, a);
+  if (x_dtype == SPK_DTYPE_U8 && y_dtype == SPK_DTYPE_SPLIT) return launch_typed<uint8_t, SplitF>(ctx, a);
   return fail(ctx, SPK_ERR_UNSUPPORTED, "conv_simt: dtype combination %d -> %d", x_dtype, y_dtype);
 }
 
@@ -367,6 +384,8 @@ int launch_maxpool(spk_ctx* ctx, int n, int h, int w, int c, int k, int stride, 
   else if (dtype == SPK_DTYPE_BF16)
     maxpool_kernel<__nv_bfloat16><<<blocks, threads, 0, ctx->stream>>>(n, h, w, c, k, stride, pad, ho, wo, ldy,
                                                                         (const __nv_bfloat16*)x, (__nv_bfloat16*)y);
+  else if (dtype == SPK_DTYPE_SPLIT)
+    maxpool_kernel<SplitF><<<blocks, threads, 0, ctx->stream>>>(n, h, w, c, k, stride, pad, ho, wo, ldy, (const SplitF*)x, (SplitF*)y);
   else
     return fail(ctx, SPK_ERR_UNSUPPORTED, "maxpool: dtype %d", dtype);
   SPK_LAUNCH_CHECK(ctx);

@@ -179,12 +179,21 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
          ((uint64_t)2 << 61);
 }
 
-template <int BN, bool DS = false>
+// MODE 0: plain.  MODE 1 (kModeDs): a second weight tile on the centre tap feeds a second accumulator (fused 1x1 / stride-2
+// shortcut).  MODE 2 (kModeSplit): FP32-accurate convolution on the bf16 tensor cores.  Activations are stored as SplitF
+// words -- bf16 hi in the low half, bf16 lo = bf16(x - hi) in the high half -- which the MMA sees as a bf16 tensor with
+// twice the channels, K index 2c = hi_c, 2c + 1 = lo_c.  Every k block is multiplied by TWO weight tiles into the same
+// accumulator: [w_hi, w_hi] (gives x_hi*w_hi + x_lo*w_hi) and [w_lo, w_lo] (x_hi*w_lo + x_lo*w_lo): the full 16-bit x
+// 16-bit product with fp32 accumulation (torch emulation of ResNet-18: |dp| <= 5e-6, experiments/emul_bf16x3_split.py).
+constexpr int kModePlain = 0, kModeDs = 1, kModeSplit = 2;
+
+template <int BN, int MODE = 0>
 struct Cfg {
+  static constexpr bool DS = MODE == kModeDs;
   static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes * (DS ? 2 : 1);
-  static constexpr int kStages = DS ? 4 : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));
-  static constexpr int kAccCols = DS ? 2 * BN : BN;            // main accumulator (+ the downsample's beside it)
+  static constexpr int kStageBytes = kABytes + kBBytes * (MODE != 0 ? 2 : 1);
+  static constexpr int kStages = MODE != 0 ? (BN >= 128 ? 4 : 6) : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int kAccCols = MODE != 0 ? 2 * BN : BN;     // main accumulator (+ the downsample's / the lo pass's beside it)
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;  // double-buffered (power of two)
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10),
@@ -192,9 +201,11 @@ struct Cfg {
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 };
 
-template <int BN, bool DS>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-  using C = Cfg<BN, DS>;
+  using C = Cfg<BN, MODE>;
+  constexpr bool DS = MODE == kModeDs;
+  constexpr bool SPLIT = MODE == kModeSplit;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&p.map_b);
     tma_prefetch_desc(&p.map_a[0]);
-    if (DS) tma_prefetch_desc(&p.map_b2);
+    if (MODE != 0) tma_prefetch_desc(&p.map_b2);
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
@@ -257,10 +268,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * C::kStageBytes;
           const bool ds = DS && tap == p.ds_tap;
-          mbar_expect_tx_w(full_bar(stage), (uint32_t)(kABytes + C::kBBytes * (ds ? 2 : 1)));
+          mbar_expect_tx_w(full_bar(stage), (uint32_t)(kABytes + C::kBBytes * ((ds || SPLIT) ? 2 : 1)));
           tma_load_4d_w(sa, &p.map_a[p.tap_map[tap]], full_bar(stage), c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
           tma_load_2d_w(sa + kABytes, &p.map_b, full_bar(stage), tap * p.cin_pad + c0, nt * BN);
           if (ds) tma_load_2d_w(sa + kABytes + C::kBBytes, &p.map_b2, full_bar(stage), c0, nt * BN);
+          if (SPLIT) tma_load_2d_w(sa + kABytes + C::kBBytes, &p.map_b2, full_bar(stage), tap * p.cin_pad + c0, nt * BN);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -289,6 +301,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
             tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (SPLIT) {  // the lo weights against the same (hi, lo) activation tile.  Own accumulator: the tensor core TRUNCATES every
+                        // fp32 accumulation (measured: rms error 4e-6 at K = 576 growing to 2e-5 at K = 4608), and these small
+                        // terms would double the number of additions into the large sum
+            const uint64_t b2_desc = smem_desc_sw128(sa + kABytes + C::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              tc_mma_w(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
           if (DS) {
             // the centre tap of a 3x3 / stride 2 / pad 1 filter samples exactly the pixels a 1x1 / stride 2
@@ -389,6 +409,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       };
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols);
+      if constexpr (SPLIT) {
+        // SplitF in / out: one 32-bit word per channel (ldy / ldres count words)
+        const uint32_t* rrow = p.res ? reinterpret_cast<const uint32_t*>(p.res) + pix * p.ldres + nt * BN : nullptr;
+        uint32_t* yrow = reinterpret_cast<uint32_t*>(p.y) + pix * p.ldy + nt * BN;
+        const float* brow = p.bias + nt * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32], vl[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld32(taddr + (uint32_t)(BN + c), vl);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c + j));
+              float f[4] = {(__uint_as_float(v[j]) + __uint_as_float(vl[j])) + b4.x, (__uint_as_float(v[j + 1]) + __uint_as_float(vl[j + 1])) + b4.y,
+                            (__uint_as_float(v[j + 2]) + __uint_as_float(vl[j + 2])) + b4.z, (__uint_as_float(v[j + 3]) + __uint_as_float(vl[j + 3])) + b4.w};
+              if (rrow) {
+                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c + j));
+                f[0] += split_load(r4.x);
+                f[1] += split_load(r4.y);
+                f[2] += split_load(r4.z);
+                f[3] += split_load(r4.w);
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              *reinterpret_cast<uint4*>(yrow + c + j) = make_uint4(split_store(f[0]), split_store(f[1]), split_store(f[2]), split_store(f[3]));
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        continue;
+      }
       drain(taddr, p.bias + nt * BN, p.res ? p.res + pix * p.ldres + nt * BN : nullptr, p.y + pix * p.ldy + nt * BN, p.relu != 0);
       if (DS) drain(taddr + (uint32_t)BN, p.bias2 + nt * BN, nullptr, p.y2 + pix * p.ldy2 + nt * BN, false);
       tc_fence_before();
@@ -435,9 +497,10 @@ int pick_bn(int cout) {
 }  // namespace
 
 struct TcConvPlan {
-  ConvGeom g;
+  ConvGeom g;  // split plans: the bf16 VIEW of the input (cin, ldx doubled); cout, ldy, ldres stay in SplitF words
   int bn = 0;
   bool ds = false;
+  bool split = false;
   TcParams prm;
   __nv_bfloat16* d_w = nullptr;
   __nv_bfloat16* d_w2 = nullptr;
@@ -485,17 +548,33 @@ bool tc_conv_ds_fusable(const ConvGeom& g3, const ConvGeom& g1) {
          g3.wo == g1.wo && g1.relu == 0 && g3.cout % 64 == 0 && g1.ldy % 8 == 0 && tc_conv_supported(g3) && tc_conv_supported(g1);
 }
 
+bool tc_conv_split_supported(const ConvGeom& g) {
+  ConvGeom v = g;
+  v.cin = 2 * g.cin;
+  v.ldx = 2 * g.ldx;
+  if (g.cin % 4 != 0 || g.ldy % 4 != 0 || g.ldres % 4 != 0) return false;  // 16-byte SplitF accesses in the epilogue
+  return tc_conv_supported(v) && pick_bn(g.cout) != 0;
+}
+
 int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, const float* d_bias, TcConvPlan** out,
-                        const float* w_ds, const float* d_bias_ds, int ldy_ds) {
-  if (!tc_conv_supported(g_max)) return fail(ctx, SPK_ERR_UNSUPPORTED, "tcgen05 convolution: unsupported geometry");
+                        const float* w_ds, const float* d_bias_ds, int ldy_ds, bool split) {
+  if (split ? (!tc_conv_split_supported(g_max) || w_ds != nullptr) : !tc_conv_supported(g_max))
+    return fail(ctx, SPK_ERR_UNSUPPORTED, "tcgen05 convolution: unsupported geometry");
   TcConvPlan* p = new TcConvPlan;
   p->g = g_max;
+  p->split = split;
+  const int cin_logical = g_max.cin;
+  if (split) {
+    p->g.cin = 2 * g_max.cin;
+    p->g.ldx = 2 * g_max.ldx;
+  }
   const ConvGeom& g = p->g;
   memset(&p->prm, 0, sizeof p->prm);
   TcParams& prm = p->prm;
   p->bn = pick_bn(g.cout);
   p->ds = w_ds != nullptr;
   if (p->ds) p->bn = g.cout % 128 == 0 ? 128 : 64;  // two accumulators per buffer: 4 * BN TMEM columns
+  if (p->split && p->bn == 256) p->bn = 128;        // two weight tiles per stage
   prm.ds_tap = p->ds ? 4 : -1;                       // (r, s) = (1, 1)
   prm.bias2 = d_bias_ds;
   prm.ldy2 = ldy_ds;
@@ -560,6 +639,21 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
   std::vector<__nv_bfloat16> wb16((size_t)g.cout * kk, __float2bfloat16(0.f));
   // plain round-to-nearest: error-diffusion rounding along K was tried and measured (torch emulation of the
   // whole network, ResNet-18 and -50 checkpoints): no robust gain, worse for 1x1 layers.
+  std::vector<__nv_bfloat16> wlo;
+  if (p->split) {
+    // [w_hi, w_hi] / [w_lo, w_lo] over the interleaved K index 2c + e
+    wlo.assign(wb16.size(), __float2bfloat16(0.f));
+    for (int o = 0; o < g.cout; ++o)
+      for (int t = 0; t < prm.taps; ++t)
+        for (int c = 0; c < cin_logical; ++c) {
+          const float v = w[((size_t)o * prm.taps + t) * cin_logical + c];
+          const __nv_bfloat16 hi = __float2bfloat16(v);
+          const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+          const size_t at = (size_t)o * kk + (size_t)t * prm.cin_pad + 2 * c;
+          wb16[at] = wb16[at + 1] = hi;
+          wlo[at] = wlo[at + 1] = lo;
+        }
+  } else
   for (int o = 0; o < g.cout; ++o)
     for (int t = 0; t < prm.taps; ++t)
       for (int c = 0; c < g.cin; ++c)
@@ -582,6 +676,26 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
     if (r != CUDA_SUCCESS) {
       tc_conv_plan_destroy(p);
       return fail(ctx, SPK_ERR_CUDA, "cuTensorMapEncodeTiled(W) failed: %d", (int)r);
+    }
+  }
+  if (p->split) {
+    cudaError_t e2 = cudaMalloc(&p->d_w2, wlo.size() * 2);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_w2, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) {
+      tc_conv_plan_destroy(p);
+      return fail(ctx, SPK_ERR_CUDA, "tcgen05 convolution: lo weight upload: %s", cudaGetErrorString(e2));
+    }
+    p->bytes += (int64_t)wlo.size() * 2;
+    cuuint64_t dims[2] = {(cuuint64_t)kk, (cuuint64_t)g.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)kk * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)p->bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(&prm.map_b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_w2, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      tc_conv_plan_destroy(p);
+      return fail(ctx, SPK_ERR_CUDA, "cuTensorMapEncodeTiled(W lo) failed: %d", (int)r);
     }
   }
   if (p->ds) {
@@ -611,14 +725,18 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
   }
   // opt in to the large dynamic shared memory on THIS device (the attribute is per device)
   cudaError_t ea = cudaSuccess;
-  if (p->ds) {
-    if (p->bn == 128) ea = cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128, true>::kSmem);
-    else ea = cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64, true>::kSmem);
+  if (p->split) {
+    if (p->bn == 128) ea = cudaFuncSetAttribute(conv_tc_kernel<128, kModeSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128, kModeSplit>::kSmem);
+    else if (p->bn == 64) ea = cudaFuncSetAttribute(conv_tc_kernel<64, kModeSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64, kModeSplit>::kSmem);
+    else ea = cudaFuncSetAttribute(conv_tc_kernel<32, kModeSplit>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32, kModeSplit>::kSmem);
+  } else if (p->ds) {
+    if (p->bn == 128) ea = cudaFuncSetAttribute(conv_tc_kernel<128, kModeDs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128, kModeDs>::kSmem);
+    else ea = cudaFuncSetAttribute(conv_tc_kernel<64, kModeDs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64, kModeDs>::kSmem);
   } else switch (p->bn) {
-    case 256: ea = cudaFuncSetAttribute(conv_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmem); break;
-    case 128: ea = cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmem); break;
-    case 64: ea = cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem); break;
-    case 32: ea = cudaFuncSetAttribute(conv_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::kSmem); break;
+    case 256: ea = cudaFuncSetAttribute(conv_tc_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256>::kSmem); break;
+    case 128: ea = cudaFuncSetAttribute(conv_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128>::kSmem); break;
+    case 64: ea = cudaFuncSetAttribute(conv_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem); break;
+    case 32: ea = cudaFuncSetAttribute(conv_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32>::kSmem); break;
   }
   if (ea != cudaSuccess) {
     tc_conv_plan_destroy(p);
@@ -641,11 +759,11 @@ void tc_conv_plan_set_reverse(TcConvPlan* p, int reverse) {
   if (p) p->prm.reverse = reverse ? 1 : 0;
 }
 
-template <int BN, bool DS = false>
+template <int BN, int MODE = 0>
 static int launch_bn(spk_ctx* ctx, const TcParams& prm) {
-  using C = Cfg<BN, DS>;
+  using C = Cfg<BN, MODE>;
   const int grid = std::min(prm.total_tiles, ctx->sm_count);
-  conv_tc_kernel<BN, DS><<<grid, kThreads, C::kSmem, ctx->stream>>>(prm);
+  conv_tc_kernel<BN, MODE><<<grid, kThreads, C::kSmem, ctx->stream>>>(prm);
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;
 }
@@ -665,7 +783,8 @@ int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void
   if (p->ds && !y_ds) return fail(ctx, SPK_ERR_INVALID, "tcgen05 convolution: fused downsample without an output");
   prm.tiles_img = (n + prm.nb - 1) / prm.nb;
   prm.total_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img * prm.tiles_n;
-  if (p->ds) return p->bn == 128 ? launch_bn<128, true>(ctx, prm) : launch_bn<64, true>(ctx, prm);
+  if (p->split) return p->bn == 128 ? launch_bn<128, kModeSplit>(ctx, prm) : p->bn == 64 ? launch_bn<64, kModeSplit>(ctx, prm) : launch_bn<32, kModeSplit>(ctx, prm);
+  if (p->ds) return p->bn == 128 ? launch_bn<128, kModeDs>(ctx, prm) : launch_bn<64, kModeDs>(ctx, prm);
   switch (p->bn) {
     case 256: return launch_bn<256>(ctx, prm);
     case 128: return launch_bn<128>(ctx, prm);

@@ -26,6 +26,8 @@ template <>
 __device__ __forceinline__ float ld<float>(const float* p) { return __ldg(p); }
 template <>
 __device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float ld<SplitF>(const SplitF* p) { return split_load(p->v); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -146,6 +148,11 @@ int launch_head(spk_ctx* ctx, const void* act, int act_dtype, int64_t n, int hw,
     head_kernel<__nv_bfloat16><<<(unsigned)n, THREADS, smem, ctx->stream>>>((const __nv_bfloat16*)act, hw, feat, w_kf, bias, k,
                                                                               softmax_scale, thr_q, logits, probs, label,
                                                                               classified);
+  } else if (act_dtype == SPK_DTYPE_SPLIT) {
+    if (smem > 48 * 1024)
+      SPK_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel<SplitF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_kernel<SplitF><<<(unsigned)n, THREADS, smem, ctx->stream>>>((const SplitF*)act, hw, feat, w_kf, bias, k, softmax_scale, thr_q,
+                                                                       logits, probs, label, classified);
   } else {
     return fail(ctx, SPK_ERR_UNSUPPORTED, "head: dtype %d", act_dtype);
   }

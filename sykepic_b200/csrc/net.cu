@@ -66,7 +66,7 @@ struct Net {
   int64_t bytes = 0;
 };
 
-static size_t dtype_size(int dt) { return dt == SPK_DTYPE_F32 ? 4 : dt == SPK_DTYPE_BF16 ? 2 : 1; }
+static size_t dtype_size(int dt) { return (dt == SPK_DTYPE_F32 || dt == SPK_DTYPE_SPLIT) ? 4 : dt == SPK_DTYPE_BF16 ? 2 : 1; }
 
 static void net_free(Net* net) {
   if (!net) return;
@@ -218,7 +218,7 @@ int spk_net_begin(spk_ctx* ctx, int target_h, int target_w, int in_channels, int
   if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_net_begin: null context");
   if (target_h < 1 || target_w < 1 || max_batch < 1) return fail(ctx, SPK_ERR_INVALID, "spk_net_begin: bad sizes");
   if (in_channels != 1 && in_channels != 3) return fail(ctx, SPK_ERR_UNSUPPORTED, "spk_net_begin: in_channels %d", in_channels);
-  if (precision != SPK_PRECISION_FP32 && precision != SPK_PRECISION_BF16)
+  if (precision != SPK_PRECISION_FP32 && precision != SPK_PRECISION_BF16 && precision != SPK_PRECISION_FP32_TC)
     return fail(ctx, SPK_ERR_INVALID, "spk_net_begin: precision %d", precision);
   SPK_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   SPK_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -229,7 +229,9 @@ int spk_net_begin(spk_ctx* ctx, int target_h, int target_w, int in_channels, int
   net->tw = target_w;
   net->in_c = in_channels;
   net->precision = precision;
-  net->act_dtype = precision == SPK_PRECISION_BF16 ? SPK_DTYPE_BF16 : SPK_DTYPE_F32;
+  // FP32_TC: activations as SplitF words (bf16 hi | lo) so that the convolutions can run on the tensor cores with
+  // fp32-level accuracy (conv_tc.cu, kModeSplit).  FP32: plain fp32 activations, CUDA-core convolutions (exact fp32 FMA).
+  net->act_dtype = precision == SPK_PRECISION_BF16 ? SPK_DTYPE_BF16 : (precision == SPK_PRECISION_FP32_TC ? SPK_DTYPE_SPLIT : SPK_DTYPE_F32);
   net->max_batch = max_batch;
   Buffer* b0 = get_buf(net, 0, true);
   b0->known = true;
@@ -566,8 +568,11 @@ int spk_net_end(spk_ctx* ctx) {
     const ConvGeom& g = op.g;
     const int K = g.kh * g.kw * g.cin;
     int impl = op.impl;
-    const bool tc_ok = net->precision == SPK_PRECISION_BF16 && net->bufs[(size_t)op.in].dtype == SPK_DTYPE_BF16 &&
-                       tc_conv_supported(g);
+    const bool split_in = net->bufs[(size_t)op.in].dtype == SPK_DTYPE_SPLIT && net->bufs[(size_t)op.out].dtype == SPK_DTYPE_SPLIT &&
+                          (op.res < 0 || net->bufs[(size_t)op.res].dtype == SPK_DTYPE_SPLIT);
+    const bool tc_ok = net->precision == SPK_PRECISION_BF16
+                           ? (net->bufs[(size_t)op.in].dtype == SPK_DTYPE_BF16 && tc_conv_supported(g))
+                           : (split_in && tc_conv_split_supported(g));
     const bool taps_only = impl == SPK_CONV_TCGEN05_TAPS;
     if (taps_only) impl = SPK_CONV_TCGEN05;
     if (impl == SPK_CONV_AUTO) impl = tc_ok ? SPK_CONV_TCGEN05 : SPK_CONV_SIMT;
@@ -580,7 +585,11 @@ int spk_net_end(spk_ctx* ctx) {
     if (impl == SPK_CONV_TCGEN05) {
       ConvGeom gm = g;
       gm.n = net->max_batch;
-      if (!taps_only && hp_conv_supported(gm)) {
+      if (net->precision != SPK_PRECISION_BF16) {
+        rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc, nullptr, nullptr, 0, true);
+        if (rc) return rc;
+        net->bytes += tc_conv_plan_bytes(op.tc);
+      } else if (!taps_only && hp_conv_supported(gm)) {
         rc = hp_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.hpair);
         if (rc) return rc;
         net->bytes += hp_conv_plan_bytes(op.hpair);
@@ -745,6 +754,16 @@ int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64
   SPK_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   if (b->dtype == SPK_DTYPE_F32) {
     SPK_CUDA_OK(ctx, cudaMemcpy(host_out, b->d, (size_t)elems * 4, cudaMemcpyDeviceToHost));
+  } else if (b->dtype == SPK_DTYPE_SPLIT) {
+    std::vector<uint32_t> tmp((size_t)elems);
+    SPK_CUDA_OK(ctx, cudaMemcpy(tmp.data(), b->d, (size_t)elems * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < elems; ++i) {
+      const uint32_t hi = tmp[(size_t)i] << 16, lo = tmp[(size_t)i] & 0xffff0000u;
+      float fh, fl;
+      memcpy(&fh, &hi, 4);
+      memcpy(&fl, &lo, 4);
+      host_out[i] = fh + fl;
+    }
   } else {
     std::vector<uint16_t> tmp((size_t)elems);
     SPK_CUDA_OK(ctx, cudaMemcpy(tmp.data(), b->d, (size_t)elems * 2, cudaMemcpyDeviceToHost));

@@ -78,6 +78,18 @@ struct ProfScope {
                        cudaGetErrorString(_e));                                             \
   } while (0)
 
+// SplitF: an fp32 value kept as two bf16 in one 32-bit word, hi = bf16(x) in the low half (the even K index of the
+// tensor-core view), lo = bf16(x - hi) in the high half: 16 mantissa bits, exact sums in fp32.
+struct SplitF {
+  uint32_t v;
+};
+__device__ __forceinline__ float split_load(uint32_t v) { return __uint_as_float(v << 16) + __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t split_store(float f) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(f);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(f - __bfloat162float(hi));
+  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+
 // get_new_dims of sykepic/train/image.py:183-198, shared by host and device code
 __host__ __device__ inline void new_dims(int h, int w, int th, int tw, int* nh, int* nw) {
   if (h > w) {
@@ -121,9 +133,11 @@ struct TcConvPlan;
 bool tc_conv_supported(const ConvGeom& g);
 // w_ds / bias_ds / ldy_ds: optional fused 1x1 stride-2 downsample branch (same input, same Cout) of a 3x3 stride-2 conv
 bool tc_conv_ds_fusable(const ConvGeom& g3x3, const ConvGeom& g1x1);
+// split = true: FP32-accurate mode on SplitF activations (bf16 hi | bf16 lo per 32-bit word); g in SplitF words
+bool tc_conv_split_supported(const ConvGeom& g);
 int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
                         const float* bias, TcConvPlan** out, const float* w_ds = nullptr, const float* bias_ds = nullptr,
-                        int ldy_ds = 0);
+                        int ldy_ds = 0, bool split = false);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y, void* y_ds = nullptr);
 int64_t tc_conv_plan_bytes(const TcConvPlan* p);

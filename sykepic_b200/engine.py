@@ -92,8 +92,10 @@ class _IdPool:
 
 
 class Engine:
-    """B200 engine for one model.  `precision`: "fp32" (CUDA-core FFMA convolutions, probabilities
-    within 1e-4 of the reference) or "bf16" (tcgen05 tensor-core convolutions, within 2e-2)."""
+    """B200 engine for one model.  `precision`: "fp32" (CUDA-core FFMA convolutions, probabilities within 1e-4 of the
+    reference), "bf16" (tcgen05 tensor-core convolutions, within 2e-2) or "fp32_tc" (fp32-level accuracy on the bf16 tensor
+    cores: activations and weights carried as bf16 hi + lo pairs; ~5x the fp32 throughput, within 1e-4 on ResNet-18, the
+    tensor core's truncating accumulation adds ~1e-5 relative per layer so deeper networks can exceed it)."""
 
     def __init__(self, spec, device=0, precision="bf16", max_batch=256, conv_impl="auto", stream=None, pre_chunk=None):
         import torch
@@ -106,7 +108,7 @@ class Engine:
             raise _lib.SpkError(_lib.SPK_ERR_CUDA, "no CUDA device: sykepic_b200 has no CPU fallback")
         self.torch = torch
         self.device = torch.device("cuda", device)
-        self.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
+        self.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16, "fp32_tc": _lib.PRECISION_FP32_TC}[precision]
         self.precision_name = precision
         self.conv_impl = {"auto": _lib.CONV_AUTO, "simt": _lib.CONV_SIMT, "tcgen05": _lib.CONV_TCGEN05, "taps": _lib.CONV_TCGEN05_TAPS}[conv_impl]
         self.max_batch = int(max_batch)

@@ -198,3 +198,19 @@ def test_densenet121_matches_oracle(tmp_path):
                 assert (err <= _bf16_tol(logits)).all(), float(err.max())
         finally:
             eng.close()
+
+
+@pytest.mark.parametrize("case", ["r18_180", "r18_224n"])
+def test_fp32_tc_probabilities(engines, case):
+    """FP32-level accuracy on the bf16 tensor cores (precision "fp32_tc": bf16 hi + lo activations and weights, fp32
+    accumulation): within the FP32 gate of 1e-4 on ResNet-18, labels identical to the fused rule on its own CSV decimals."""
+    eng = engines(case, "fp32_tc")
+    eng.set_thresholds(_thresholds("thresholds-zero"))
+    for bname, b in case_bins(case):
+        g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
+        rid, probs, label, classified = eng.run_bin(b["adc_text"], b["roi_bytes"], want_labels=True)
+        assert rid.tolist() == g["roi_id"].tolist()
+        assert np.abs(probs - g["probs"]).max() <= FP32_PROB_TOL, float(np.abs(probs - g["probs"]).max())
+        vals = o_pred.parse_prob_csv_text(engine.format_prob_csv(eng.spec.classes, rid, probs).decode())[2]
+        idx, flag = prediction.predict_array(vals, eng.spec.classes, _thresholds("thresholds-zero"))
+        assert label.tolist() == idx.tolist() and classified.tolist() == flag.tolist()
