@@ -419,7 +419,7 @@ def run_b200(args):
             "kernel_ms_per_step": step_ms,
             "wall_s_timed_region": wall,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only (under torchrun OMP_NUM_THREADS is 1)
             rate, n_done, cores = cpu_port_rate(args, mdir, chunks, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{n_done} ROIs of the same synthetic batch (oracle: numpy transform + torch-CPU fp32 forward)",

@@ -44,7 +44,10 @@ class _PinnedPool:
                 if t.numel() >= nbytes:
                     return self.free.pop(i)
         cap = max(1 << 20, int(nbytes * 1.25))
-        return self.torch.empty(cap, dtype=self.torch.uint8, pin_memory=True)
+        try:
+            return self.torch.empty(cap, dtype=self.torch.uint8, pin_memory=True)
+        except RuntimeError:  # no CUDA runtime (host-only unit tests): an ordinary buffer serves the same interface
+            return self.torch.empty(cap, dtype=self.torch.uint8)
 
     def put(self, t):
         with self.lock:
