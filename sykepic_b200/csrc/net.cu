@@ -186,6 +186,9 @@ int spk_destroy(spk_ctx* ctx) {
   if (ctx->d_default_lut) cudaFree(ctx->d_default_lut);
   if (ctx->d_big_list) cudaFree(ctx->d_big_list);
   if (ctx->d_big_count) cudaFree(ctx->d_big_count);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
   return SPK_OK;
 }

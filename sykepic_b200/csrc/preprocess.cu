@@ -568,6 +568,44 @@ __device__ __forceinline__ void image_rows_fast(const SrcView<kShared> S, int w,
   }
 }
 
+// Geometry of ROI n and whether the warp kernel takes it.  The warp kernel resizes what IFCB ROIs almost always are:
+// bilinear (not the identity / exact-2x special cases), horizontal scale <= 1.6 so that the taps of 4 columns fit an
+// 8-byte window, and small.  Everything else -- ~1 % of real ROIs -- goes to the cluster kernel.
+struct RoiGeom {
+  int w, h, nw, nh;
+  long long start, total;
+  bool valid, fast, staged;
+  int mis;
+};
+__device__ __forceinline__ RoiGeom roi_geom(const Params& p, long long n) {
+  RoiGeom g;
+  g.w = p.w[n];
+  g.h = p.h[n];
+  g.start = p.start[n];
+  g.valid = (g.w >= 1) && (g.h >= 1) && (g.w < 65536) && (g.start >= 0) && (g.start + (long long)g.w * g.h <= p.roi_len);
+  g.nh = g.nw = 0;
+  if (g.valid) {
+    new_dims(g.h, g.w, p.th, p.tw, &g.nh, &g.nw);
+    g.valid = (g.nh >= 1) && (g.nw >= 1) && (g.nh <= p.th) && (g.nw <= p.tw);
+  }
+  if (!g.valid) g.nh = g.nw = 0;
+  g.total = g.valid ? (long long)g.w * g.h : 0;
+  const uint8_t* src = p.roi + (g.valid ? g.start : 0);
+  g.mis = (int)((unsigned long long)src & 15);
+  g.staged = g.total > 0 && (g.mis + g.total <= kStage + 16);
+  g.fast = !g.valid || ((g.total <= p.big_bytes) && !(g.nw == g.w && g.nh == g.h) && !(g.w == 2 * g.nw && g.h == 2 * g.nh) &&
+                        ((long long)g.w * 10 <= (long long)g.nw * 16) && (g.staged || (src + g.total + 12 <= p.roi + p.roi_len)));
+  return g;
+}
+
+// one thread per ROI: queue what the warp kernel will not take, so that the cluster kernel can run BESIDE it (second stream)
+__global__ void preprocess_classify_kernel(Params p, long long n_rois) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_rois) return;
+  const RoiGeom g = roi_geom(p, n);
+  if (!g.fast) p.big_list[atomicAdd(p.big_count, 1u)] = (int)n;
+}
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) preprocess_u8_kernel(Params p, long long n_rois) {
   __shared__ __align__(16) uint8_t stage_s[kWarpsPerCta][kStage + 32];  // + misalignment (<= 15) + window over-read (<= 11)
   __shared__ __align__(16) unsigned hist_s[kWarpsPerCta][4 * 128];  // [sub-histogram][bin pair]: two 16-bit counters per word;
@@ -582,34 +620,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 5) preprocess_u8_kernel(Par
   const int part = (int)(item - n * parts);
   if (n >= n_rois) return;
   const int th = p.th, tw = p.tw;
-  const int w = p.w[n], h = p.h[n];
-  const long long start = p.start[n];
-  bool valid = (w >= 1) && (h >= 1) && (w < 65536) && (start >= 0) && (start + (long long)w * h <= p.roi_len);
-  int nh = 0, nw = 0;
-  if (valid) {
-    new_dims(h, w, th, tw, &nh, &nw);
-    valid = (nh >= 1) && (nw >= 1) && (nh <= th) && (nw <= tw);
-  }
-  if (!valid) {
-    if (lane == 0 && part == 0) atomicAdd(p.faults, 1ULL);
-    nh = 0;
-    nw = 0;
-  }
-  const long long total = valid ? (long long)w * h : 0;
-  const uint8_t* src = p.roi + (valid ? start : 0);
-  const int mis = (int)((unsigned long long)src & 15);
-  const bool staged = total > 0 && (mis + total <= kStage + 16);
-  if (valid) {
-    // This kernel resizes what IFCB ROIs almost always are: bilinear (not the identity / exact-2x special cases),
-    // horizontal scale <= 1.6 so that the taps of 4 columns fit an 8-byte window, and small.
-    // Everything else -- ~1 % of ROIs -- is queued for the cluster kernel.
-    const bool fast = (total <= p.big_bytes) && !(nw == w && nh == h) && !(w == 2 * nw && h == 2 * nh) &&
-                      ((long long)w * 10 <= (long long)nw * 16) && (staged || (src + total + 12 <= p.roi + p.roi_len));
-    if (!fast) {
-      if (lane == 0 && part == 0) p.big_list[atomicAdd(p.big_count, 1u)] = (int)n;
-      return;
-    }
-  }
+  const RoiGeom g = roi_geom(p, n);
+  if (!g.fast) return;  // queued by preprocess_classify_kernel for the cluster kernel
+  const int w = g.w, h = g.h, nw = g.nw, nh = g.nh;
+  const bool valid = g.valid, staged = g.staged;
+  const long long total = g.total;
+  const int mis = g.mis;
+  const uint8_t* src = p.roi + (valid ? g.start : 0);
+  if (!valid && lane == 0 && part == 0) atomicAdd(p.faults, 1ULL);
   uint8_t* out = (uint8_t*)p.out + n * (long long)th * tw;
   const int top = (th - nh) / 2, left = (tw - nw) / 2;
   const bool has_border = (nh < th) || (nw < tw);
@@ -814,15 +832,28 @@ extern "C" int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t ro
     }
     if (!ctx->d_big_count) SPK_CUDA_OK(ctx, cudaMalloc(&ctx->d_big_count, sizeof(unsigned)));
     SPK_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_big_count, 0, sizeof(unsigned), ctx->stream));
+    if (!ctx->stream2) {
+      SPK_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+      SPK_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      SPK_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
     p.big_list = ctx->d_big_list;
     p.big_count = ctx->d_big_count;
     p.big_bytes = kBigBytes;
+    preprocess_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(p, (long long)n);
+    SPK_LAUNCH_CHECK(ctx);
+    // the cluster kernel (heavy tail) runs on a second stream beside the warp kernel
+    SPK_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    SPK_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    Params pb = p;
+    pb.slabs = kBigSlabs;
+    preprocess_big_kernel<<<kBigClusters * kBigSlabs, kThreads, kHBytes, ctx->stream2>>>(pb);
+    SPK_LAUNCH_CHECK(ctx);
+    SPK_CUDA_OK(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
     p.slabs = n <= 1024 ? 4 : n <= 2048 ? 2 : 1;  // warps per ROI
     const long long items = n * p.slabs;
     preprocess_u8_kernel<<<(unsigned)((items + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, (long long)n);
-    SPK_LAUNCH_CHECK(ctx);
-    p.slabs = kBigSlabs;
-    preprocess_big_kernel<<<kBigClusters * kBigSlabs, kThreads, kHBytes, ctx->stream>>>(p);
+    SPK_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   } else {
     preprocess_kernel<<<(unsigned)blocks, kThreads, kHBytes, ctx->stream>>>(p);
   }

@@ -40,6 +40,8 @@ struct spk_ctx {
   int* d_big_list = nullptr;               // K1: queue of heavy-tail ROIs for the cluster kernel
   unsigned* d_big_count = nullptr;
   long long big_cap = 0;
+  cudaStream_t stream2 = nullptr;          // K1: the cluster kernel runs beside the warp kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   spk::Net* net = nullptr;
   int sm_count = 148;
   bool profiling = false;
