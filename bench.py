@@ -165,6 +165,11 @@ def run_reference(args):
         return 0
     import torch
 
+    # all the host threads this process may use (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     args.batch = args.batch or (256 if args.arch == "resnet18" else 512)
     tmp = tempfile.mkdtemp(prefix="spk_bench_")
     mdir = model_dir(args, tmp)

@@ -106,6 +106,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(a_full(s), 1);
@@ -149,6 +150,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
       for (int ch = 0; ch < p.kchunks; ++ch)
         for (int tap = 0; tap < 9; ++tap)
           tma2_load_2d(b_s + (uint32_t)(ch * 9 + tap) * kBHalf, &p.map_w, bfull_leader, tap * p.cin + ch * 64, (int)rank * (BN / 2));
+      pdl_wait();  // the filter bank does not depend on the previous kernel; the activations do
       int as = 0;
       uint32_t aph = 0;
       for (int u = cluster_id; u < p.units; u += n_clusters) {
@@ -233,6 +235,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
     const int j = q * 32 + lane;  // TMEM lane == linear halo-pitch pixel of this CTA's tile
     const int jr = j / p.pitch, jc = j - jr * p.pitch;
     const uint32_t t_empty_leader = mapa_rank(t_empty(0), 0);
+    pdl_wait();  // residual reads and output writes wait for the previous kernel
     int acc = 0;
     uint32_t accph = 0;
     // residual: this thread's 32 channels of every slab, straight from global memory into registers ONE UNIT AHEAD
@@ -476,9 +479,9 @@ int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void
     prm.trace = d_trace;
   }
   if (g.cout == 128)
-    conv3x3_hp_kernel<128><<<2 * clusters, kThreads, p->smem, ctx->stream>>>(prm);
+    SPK_CUDA_OK(ctx, launch_pdl(conv3x3_hp_kernel<128>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   else
-    conv3x3_hp_kernel<64><<<2 * clusters, kThreads, p->smem, ctx->stream>>>(prm);
+    SPK_CUDA_OK(ctx, launch_pdl(conv3x3_hp_kernel<64>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   SPK_LAUNCH_CHECK(ctx);
   if (prm.trace) {
     --trace_left;

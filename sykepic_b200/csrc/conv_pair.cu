@@ -91,6 +91,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(full_bar(s), 1);   // used in the leader only: its producer's arrive.expect_tx
@@ -114,6 +115,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
   cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything below reads / writes tensors the previous kernel may still be using
 
   // unit -> this CTA's M tile (box origin) and the N tile
   auto decode = [&](int u, int& nt, int& w0, int& h0, int& n0) {
@@ -523,9 +525,9 @@ int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const 
     prm.trace = d_trace;
   }
   if (p->bn == 256)
-    conv_pair_kernel<256><<<2 * clusters, kThreads, p->smem, ctx->stream>>>(prm);
+    SPK_CUDA_OK(ctx, launch_pdl(conv_pair_kernel<256>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   else
-    conv_pair_kernel<128><<<2 * clusters, kThreads, p->smem, ctx->stream>>>(prm);
+    SPK_CUDA_OK(ctx, launch_pdl(conv_pair_kernel<128>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   SPK_LAUNCH_CHECK(ctx);
   if (prm.trace) {
     --trace_left;

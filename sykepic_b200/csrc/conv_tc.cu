@@ -28,6 +28,7 @@
 #include <cstring>
 
 #include "spk_internal.h"
+#include "tc_common.cuh"  // only tc::pdl_* / tc::launch_pdl are used here; this file keeps its own PTX wrappers
 
 namespace spk {
 namespace {
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
+  tc::pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  tc::pdl_wait();  // everything below reads / writes tensors the previous kernel may still be using
 
   const int kblocks = p.taps * p.kchunks;
 
@@ -763,7 +766,7 @@ template <int BN, int MODE = 0>
 static int launch_bn(spk_ctx* ctx, const TcParams& prm) {
   using C = Cfg<BN, MODE>;
   const int grid = std::min(prm.total_tiles, ctx->sm_count);
-  conv_tc_kernel<BN, MODE><<<grid, kThreads, C::kSmem, ctx->stream>>>(prm);
+  SPK_CUDA_OK(ctx, tc::launch_pdl(conv_tc_kernel<BN, MODE>, dim3(grid), dim3(kThreads), C::kSmem, ctx->stream, prm));
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;
 }

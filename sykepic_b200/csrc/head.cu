@@ -13,6 +13,7 @@
 #include <climits>
 
 #include "spk_internal.h"
+#include "tc_common.cuh"  // tc::pdl_* / tc::launch_pdl
 
 namespace spk {
 namespace {
@@ -54,6 +55,8 @@ __global__ void __launch_bounds__(THREADS) head_kernel(const T* act, int hw, int
   __shared__ float s_max, s_sum;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n = blockIdx.x;
+  tc::pdl_trigger();
+  tc::pdl_wait();  // the activations are the previous kernel's output
 
   // global average pool: sum over the hw positions in position order, then divide (fp32)
   const T* a = act + n * (long long)hw * F;
@@ -140,19 +143,18 @@ int launch_head(spk_ctx* ctx, const void* act, int act_dtype, int64_t n, int hw,
   if (act_dtype == SPK_DTYPE_F32) {
     if (smem > 48 * 1024)
       SPK_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_kernel<float><<<(unsigned)n, THREADS, smem, ctx->stream>>>((const float*)act, hw, feat, w_kf, bias, k, softmax_scale,
-                                                                      thr_q, logits, probs, label, classified);
+    SPK_CUDA_OK(ctx, tc::launch_pdl(head_kernel<float>, dim3((unsigned)n), dim3(THREADS), smem, ctx->stream, (const float*)act, hw, feat, w_kf,
+                                    bias, k, softmax_scale, thr_q, logits, probs, label, classified));
   } else if (act_dtype == SPK_DTYPE_BF16) {
     if (smem > 48 * 1024)
       SPK_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_kernel<__nv_bfloat16><<<(unsigned)n, THREADS, smem, ctx->stream>>>((const __nv_bfloat16*)act, hw, feat, w_kf, bias, k,
-                                                                              softmax_scale, thr_q, logits, probs, label,
-                                                                              classified);
+    SPK_CUDA_OK(ctx, tc::launch_pdl(head_kernel<__nv_bfloat16>, dim3((unsigned)n), dim3(THREADS), smem, ctx->stream,
+                                    (const __nv_bfloat16*)act, hw, feat, w_kf, bias, k, softmax_scale, thr_q, logits, probs, label, classified));
   } else if (act_dtype == SPK_DTYPE_SPLIT) {
     if (smem > 48 * 1024)
       SPK_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel<SplitF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_kernel<SplitF><<<(unsigned)n, THREADS, smem, ctx->stream>>>((const SplitF*)act, hw, feat, w_kf, bias, k, softmax_scale, thr_q,
-                                                                       logits, probs, label, classified);
+    SPK_CUDA_OK(ctx, tc::launch_pdl(head_kernel<SplitF>, dim3((unsigned)n), dim3(THREADS), smem, ctx->stream, (const SplitF*)act, hw, feat, w_kf,
+                                    bias, k, softmax_scale, thr_q, logits, probs, label, classified));
   } else {
     return fail(ctx, SPK_ERR_UNSUPPORTED, "head: dtype %d", act_dtype);
   }

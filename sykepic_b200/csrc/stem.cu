@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  pdl_trigger();
+  pdl_wait();  // the strip is the previous kernel's output
   const int image = blockIdx.x / p.strips;
   const int strip = blockIdx.x - image * p.strips;
   const int p0 = strip * kPoolRowsPerStrip;
@@ -437,7 +439,7 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     cudaMemsetAsync(d_trace, 0, 16 * 64 * sizeof(long long), ctx->stream);
     p.trace = d_trace;
   }
-  stem_pool_kernel<<<(unsigned)(n * p.strips), kThreads, smem, ctx->stream>>>(cache.map, p);
+  SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   SPK_LAUNCH_CHECK(ctx);
   if (p.trace) {
     --trace_left;

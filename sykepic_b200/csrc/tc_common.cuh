@@ -8,6 +8,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 namespace spk {
 namespace tc {
@@ -195,6 +196,29 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- programmatic dependent launch: a kernel launched with launch_pdl may start while its predecessor in the stream is
+// still running (once every CTA of the predecessor has executed pdl_trigger or exited).  Its CTAs take over the SMs as
+// they free up and run their prologue (barrier init, TMEM allocation, resident weights); pdl_wait then blocks until the
+// predecessor has completed and its memory is visible.  Hides the launch gap between the ~20 back-to-back kernels of a step.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool off = getenv("SPK_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
