@@ -103,10 +103,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// per-CTA clock trace, compiled in only with -DSPK_STEM_TRACE_BUILD (the modulo and the clock reads cost ~40 of the ~240
+// instructions an epilogue warp spends per conv row)
+#ifdef SPK_STEM_TRACE_BUILD
 #define STEM_TRACE(slot)                                                                         \
   do {                                                                                           \
     if (p.trace && (blockIdx.x % 1000) == 500) p.trace[(blockIdx.x / 1000) * 64 + (slot)] = clock64(); \
   } while (0)
+#else
+#define STEM_TRACE(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const StemParams p) {
   extern __shared__ unsigned char smem_raw[];
