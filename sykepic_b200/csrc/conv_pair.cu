@@ -224,7 +224,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
     uint32_t accph = 0, rph = 0;
     int tr = 0;
     const bool tracing = p.trace != nullptr && blockIdx.x == 10 && et == 0;
+#ifdef SPK_PAIR_TRACE_BUILD  // epilogue clock trace: compiled in on request only
 #define PAIR_TRACE() do { if (tracing && tr < 250) p.trace[tr++] = clock64(); } while (0)
+#else
+#define PAIR_TRACE() do { (void)tracing; (void)tr; } while (0)
+#endif
     for (int u = cluster_id; u < p.units; u += n_clusters) {
       int nt, w0, h0, n0;
       decode(u, nt, w0, h0, n0);
