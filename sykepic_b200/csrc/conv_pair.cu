@@ -48,7 +48,10 @@ constexpr size_t kSmemMax = 232448;
 struct alignas(64) PairParams {
   CUtensorMap map_a[4];
   CUtensorMap map_b, map_y, map_res;
+  CUtensorMap map_b2, map_y2;  // fused 1x1 / stride-2 shortcut: weights [Cout][cin_pad] on the centre tap's A tiles, its own output
   const float* bias;
+  const float* bias2;
+  int ds_tap;
   int n, ho, wo, cout, relu, has_res;
   int wb, hb, nb;
   int tiles_w, tiles_h, tiles_img, tiles_n;
@@ -60,11 +63,15 @@ struct alignas(64) PairParams {
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
 
-template <int BN>
+// DS: the block's 1x1 / stride-2 shortcut rides on the centre tap of this 3x3 / stride-2 convolution (same pixels): a second
+// weight half-tile per centre-tap stage, a second accumulator beside the main one (BN = 128: 2 x 2 x 128 TMEM columns).
+template <int BN, bool DS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pair_kernel(const __grid_constant__ PairParams p) {
+  static_assert(!DS || BN == 128, "the fused shortcut needs two accumulators per buffer");
   constexpr int kBHalfBytes = (BN / 2) * kBK * 2;
-  constexpr int kStageBytes = kABytes + kBHalfBytes;
-  constexpr int kTmemCols = 2 * BN;  // double-buffered accumulator: 512 or 256 columns
+  constexpr int kStageBytes = kABytes + kBHalfBytes * (DS ? 2 : 1);
+  constexpr int kAccCols = DS ? 2 * BN : BN;
+  constexpr int kTmemCols = 2 * kAccCols;  // double-buffered accumulator(s): 512 or 256 columns
   constexpr int kSlabs = BN / 64;
   constexpr uint32_t kIdesc = idesc_bf16(256, BN);
 
@@ -108,6 +115,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
     tma_prefetch_desc(&p.map_b);
     tma_prefetch_desc(&p.map_y);
     if (p.has_res) tma_prefetch_desc(&p.map_res);
+    if (DS) {
+      tma_prefetch_desc(&p.map_b2);
+      tma_prefetch_desc(&p.map_y2);
+    }
   }
   if (warp == 1) tmem2_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
   for (int i = threadIdx.x; i < p.cout; i += kThreads) bias_sm[i] = __ldg(p.bias + i);
@@ -152,9 +163,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * kStageBytes;
           const uint32_t full_leader = mapa_rank(full_bar(stage), 0);
-          if (leader) mbar_expect_tx_w(full_bar(stage), 2u * kStageBytes);  // both CTAs' bytes land on this barrier
+          const bool ds = DS && tap == p.ds_tap;
+          if (leader) mbar_expect_tx_w(full_bar(stage), 2u * (uint32_t)(kABytes + kBHalfBytes * (ds ? 2 : 1)));  // both CTAs' bytes land on this barrier
           tma2_load_4d_w(sa, &p.map_a[p.tap_map[tap]], full_leader, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
           tma2_load_2d_w(sa + kABytes, &p.map_b, full_leader, tap * p.cin_pad + c0, nt * BN + (int)rank * (BN / 2));
+          if (ds) tma2_load_2d_w(sa + kABytes + kBHalfBytes, &p.map_b2, full_leader, c0, nt * BN + (int)rank * (BN / 2));
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -170,7 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
       for (int u = cluster_id; u < p.units; u += n_clusters) {
         mbar_wait_cluster(t_empty(acc), accph ^ 1u);  // both CTAs have drained this accumulator buffer
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccCols);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -180,6 +193,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)
             tc2_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), kIdesc, (kb | k) != 0 ? 1u : 0u);
+          if (DS) {
+            const int tap = kb / p.kchunks;
+            if (tap == p.ds_tap) {
+              const int c = kb - tap * p.kchunks;
+              const uint64_t b2_desc = smem_desc_sw128(sa + kABytes + kBHalfBytes);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k)
+                tc2_mma_w(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), kIdesc, (c | k) != 0 ? 1u : 0u);
+            }
+          }
           tc2_commit_mc_w(empty_bar(stage), 3);  // frees the stage in both CTAs
           if (++stage == p.stages) {
             stage = 0;
@@ -237,12 +260,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
       tc_fence_after();
       PAIR_TRACE();
 #pragma unroll 1
-      for (int slab = 0; slab < kSlabs; ++slab) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * 64 + half * 32);
+      for (int s2 = 0; s2 < kSlabs * (DS ? 2 : 1); ++s2) {
+        const bool dsp = DS && s2 >= kSlabs;  // the shortcut's accumulator: its own bias and output, no residual, no ReLU
+        const int slab = dsp ? s2 - kSlabs : s2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + (dsp ? BN : 0) + slab * 64 + half * 32);
         uint32_t v[32];
         tmem_ld32(taddr, v);
         tmem_ld_wait();
-        if (slab == kSlabs - 1) {  // accumulator buffer drained: tell the leader's MMA thread
+        if (s2 == kSlabs * (DS ? 2 : 1) - 1) {  // accumulator buffer drained: tell the leader's MMA thread
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(mapa_rank(t_empty(acc), 0));
@@ -250,12 +275,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
         PAIR_TRACE();
         if (et == 0) tma_store_wait_read<1>();  // staging slot `os` was last read by the store issued two slabs ago
         PAIR_TRACE();
-        if (p.has_res) mbar_wait(r_full(rs), rph);
+        const bool with_res = p.has_res && !dsp;
+        if (with_res) mbar_wait(r_full(rs), rph);
         PAIR_TRACE();
         named_bar_sync(1, kEpiThreads);
         PAIR_TRACE();
         {
-          const float* bsm = bias_sm + nt * BN + slab * 64 + half * 32;
+          const float* bsm = dsp ? p.bias2 + nt * BN + slab * 64 + half * 32 : bias_sm + nt * BN + slab * 64 + half * 32;
           unsigned char* orow_p = gen + out_off + (uint32_t)os * kIoSlot + (uint32_t)row * 128u;
           const unsigned char* rrow_p = gen + res_off + (uint32_t)rs * kIoSlot + (uint32_t)row * 128u;
 #pragma unroll
@@ -266,7 +292,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c4 * 8 + e]) + bv[e];
             const uint32_t chunk = ((uint32_t)(half * 4 + c4) ^ sw) << 4;
-            if (p.has_res) {
+            if (with_res) {
               const uint4 r4 = *reinterpret_cast<const uint4*>(rrow_p + chunk);
               const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r4);
 #pragma unroll
@@ -276,7 +302,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
                 f[2 * t + 1] += rf.y;
               }
             }
-            if (p.relu) {
+            if (p.relu && !dsp) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
@@ -292,7 +318,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
             *reinterpret_cast<uint4*>(orow_p + chunk) = o;
           }
         }
-        if (p.has_res) {
+        if (with_res) {
           __syncwarp();
           if (lane == 0) mbar_arrive(r_empty(rs));
           if (++rs == 2) {
@@ -305,7 +331,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
         named_bar_sync(2, kEpiThreads);
         PAIR_TRACE();
         if (et == 0) {
-          tma_store_4d(&p.map_y, base + out_off + (uint32_t)os * kIoSlot, nt * BN + slab * 64, w0, h0, n0);
+          tma_store_4d(dsp ? &p.map_y2 : &p.map_y, base + out_off + (uint32_t)os * kIoSlot, nt * BN + slab * 64, w0, h0, n0);
           tma_store_commit();
         }
         os ^= 1;
@@ -331,6 +357,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
 struct PairConvPlan {
   ConvGeom g;
   int bn = 0;
+  bool ds = false;
+  __nv_bfloat16* d_w2 = nullptr;
+  const void* y2_ptr = nullptr;
+  int ldy2 = 0;
   PairParams prm;
   __nv_bfloat16* d_w = nullptr;
   int64_t bytes = 0;
@@ -348,14 +378,19 @@ bool pair_conv_supported(const ConvGeom& g) {
   return true;
 }
 
-int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, const float* d_bias, PairConvPlan** out) {
+int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, const float* d_bias, PairConvPlan** out,
+                          const float* w_ds, const float* d_bias_ds, int ldy_ds) {
   if (!pair_conv_supported(g_max)) return fail(ctx, SPK_ERR_UNSUPPORTED, "pair convolution: unsupported geometry");
   PairConvPlan* p = new PairConvPlan;
   p->g = g_max;
   const ConvGeom& g = p->g;
   memset(&p->prm, 0, sizeof p->prm);
   PairParams& prm = p->prm;
-  p->bn = g.cout % 256 == 0 ? 256 : 128;  // revised below once the tile box is known (wave quantisation)
+  p->ds = w_ds != nullptr;
+  p->ldy2 = ldy_ds;
+  prm.ds_tap = p->ds ? 4 : -1;  // (r, s) = (1, 1) of a 3x3 / pad 1 filter
+  prm.bias2 = d_bias_ds;
+  p->bn = (g.cout % 256 == 0 && !p->ds) ? 256 : 128;  // (the fused shortcut takes a second accumulator: N = 128)
   prm.bias = d_bias;
   prm.ho = g.ho;
   prm.wo = g.wo;
@@ -385,7 +420,7 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
   prm.tiles_h = (g.ho + prm.hb - 1) / prm.hb;
   // ---- N tile: 256 halves the A re-reads, but a layer with few M tiles (7x7 maps: 98 pairs x N tiles at batch 256) then
   // leaves most of the 74 clusters idle in its last round; pick the width with the shorter schedule at the planned batch
-  if (g.cout % 256 == 0 && getenv("SPK_PAIR_BN_AUTO")) {  // measured (512->512 @7x7, batch 256): 0.063 ms at N = 128 vs 0.058-0.062 at N = 256; off
+  if (g.cout % 256 == 0 && !p->ds && getenv("SPK_PAIR_BN_AUTO")) {  // measured (512->512 @7x7, batch 256): 0.063 ms at N = 128 vs 0.058-0.062 at N = 256; off
     const long long m_tiles = (long long)prm.tiles_w * prm.tiles_h * ((g.n + prm.nb - 1) / prm.nb);
     const long long pairs = (m_tiles + 1) / 2, clusters = std::max(1, ctx->sm_count / 2);
     auto rounds = [&](int bn) { return (pairs * (g.cout / bn) + clusters - 1) / clusters; };
@@ -421,7 +456,7 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
     }
 
   // ---- shared memory: stages under the budget
-  const size_t stage = (size_t)kABytes + (size_t)(p->bn / 2) * kBK * 2;
+  const size_t stage = (size_t)kABytes + (size_t)(p->bn / 2) * kBK * 2 * (p->ds ? 2 : 1);
   prm.res_slots = g.ldres ? 2 : 0;
   const size_t fixed = 1024 + (size_t)(2 + prm.res_slots) * kIoSlot + (size_t)g.cout * 4 + 16 + 8 * (2 * kMaxStages + 8) + 16;
   prm.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / stage);
@@ -458,7 +493,33 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
       return fail(ctx, SPK_ERR_CUDA, "pair convolution: cuTensorMapEncodeTiled(W) failed: %d", (int)r);
     }
   }
-  cudaError_t ea = p->bn == 256
+  if (p->ds) {
+    // shortcut weights: bf16 [Cout][cin_pad]
+    const size_t k1 = (size_t)prm.cin_pad;
+    std::vector<__nv_bfloat16> w2((size_t)g.cout * k1, __float2bfloat16(0.f));
+    for (int o = 0; o < g.cout; ++o)
+      for (int c = 0; c < g.cin; ++c) w2[(size_t)o * k1 + c] = __float2bfloat16(w_ds[(size_t)o * g.cin + c]);
+    cudaError_t e2 = cudaMalloc(&p->d_w2, w2.size() * 2);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_w2, w2.data(), w2.size() * 2, cudaMemcpyHostToDevice);
+    if (e2 != cudaSuccess) {
+      pair_conv_plan_destroy(p);
+      return fail(ctx, SPK_ERR_CUDA, "pair convolution: shortcut weight upload: %s", cudaGetErrorString(e2));
+    }
+    p->bytes += (int64_t)w2.size() * 2;
+    cuuint64_t dims[2] = {(cuuint64_t)k1, (cuuint64_t)g.cout};
+    cuuint64_t strides[1] = {(cuuint64_t)k1 * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(p->bn / 2)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(&prm.map_b2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p->d_w2, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      pair_conv_plan_destroy(p);
+      return fail(ctx, SPK_ERR_CUDA, "pair convolution: cuTensorMapEncodeTiled(W shortcut) failed: %d", (int)r);
+    }
+  }
+  cudaError_t ea = p->ds ? cudaFuncSetAttribute(conv_pair_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
+                   : p->bn == 256
                        ? cudaFuncSetAttribute(conv_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
                        : cudaFuncSetAttribute(conv_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
   if (ea != cudaSuccess) {
@@ -472,6 +533,7 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
 void pair_conv_plan_destroy(PairConvPlan* p) {
   if (!p) return;
   if (p->d_w) cudaFree(p->d_w);
+  if (p->d_w2) cudaFree(p->d_w2);
   delete p;
 }
 
@@ -481,7 +543,7 @@ void pair_conv_plan_set_reverse(PairConvPlan* p, int reverse) {
   if (p) p->prm.reverse = reverse ? 1 : 0;
 }
 
-int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y) {
+int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y, void* y_ds) {
   if (n <= 0) return SPK_OK;
   const ConvGeom& g = p->g;
   if (n > g.n) return fail(ctx, SPK_ERR_CAPACITY, "pair convolution: batch %d > planned %d", n, g.n);
@@ -507,6 +569,14 @@ int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const 
     if (r != CUDA_SUCCESS) return fail(ctx, SPK_ERR_CUDA, "pair convolution: tensor map (y) failed: %d", (int)r);
     p->y_ptr = y;
   }
+  if (p->ds) {
+    if (!y_ds) return fail(ctx, SPK_ERR_INVALID, "pair convolution: fused shortcut without an output");
+    if (y_ds != p->y2_ptr) {
+      CUresult r = encode_nhwc_bf16(&prm.map_y2, y_ds, g.cout, g.wo, g.ho, g.n, p->ldy2, 64, prm.wb, prm.hb, prm.nb);
+      if (r != CUDA_SUCCESS) return fail(ctx, SPK_ERR_CUDA, "pair convolution: tensor map (shortcut output) failed: %d", (int)r);
+      p->y2_ptr = y_ds;
+    }
+  }
   if (res && res != p->res_ptr) {
     CUresult r = encode_nhwc_bf16(&prm.map_res, res, g.cout, g.wo, g.ho, g.n, g.ldres, 64, prm.wb, prm.hb, prm.nb);
     if (r != CUDA_SUCCESS) return fail(ctx, SPK_ERR_CUDA, "pair convolution: tensor map (residual) failed: %d", (int)r);
@@ -528,10 +598,12 @@ int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const 
     cudaMemsetAsync(d_trace, 0, 256 * sizeof(long long), ctx->stream);
     prm.trace = d_trace;
   }
-  if (p->bn == 256)
-    SPK_CUDA_OK(ctx, launch_pdl(conv_pair_kernel<256>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
+  if (p->ds)
+    SPK_CUDA_OK(ctx, launch_pdl(conv_pair_kernel<128, true>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
+  else if (p->bn == 256)
+    SPK_CUDA_OK(ctx, launch_pdl(conv_pair_kernel<256, false>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   else
-    SPK_CUDA_OK(ctx, launch_pdl(conv_pair_kernel<128>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
+    SPK_CUDA_OK(ctx, launch_pdl(conv_pair_kernel<128, false>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   SPK_LAUNCH_CHECK(ctx);
   if (prm.trace) {
     --trace_left;

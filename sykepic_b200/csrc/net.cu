@@ -607,9 +607,15 @@ int spk_net_end(spk_ctx* ctx) {
       } else if (op.ds_out >= 0) {
         rc = upload(ctx, op.ds_b.data(), op.ds_b.size(), &op.d_bias_ds);
         if (rc) return rc;
-        rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc, op.ds_w.data(), op.d_bias_ds, op.ds_ld);
-        if (rc) return rc;
-        net->bytes += tc_conv_plan_bytes(op.tc);
+        if (!taps_only && pair_conv_supported(gm) && !getenv("SPK_NO_PAIR_DS")) {
+          rc = pair_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.pair, op.ds_w.data(), op.d_bias_ds, op.ds_ld);
+          if (rc) return rc;
+          net->bytes += pair_conv_plan_bytes(op.pair);
+        } else {
+          rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc, op.ds_w.data(), op.d_bias_ds, op.ds_ld);
+          if (rc) return rc;
+          net->bytes += tc_conv_plan_bytes(op.tc);
+        }
         std::vector<float>().swap(op.ds_w);
         std::vector<float>().swap(op.ds_b);
       } else {
@@ -678,14 +684,15 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
                        (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * ((op.res >= 0 ? 2 : 1) + ds_taps) +
                            (double)g.cout * (g.kh * g.kw + ds_taps) * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
                        "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
-                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.hpair ? " [halo pair]" : op.halo ? " [halo]" : (op.pair ? " [pair]" : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : "")));
+                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.hpair ? " [halo pair]" : op.halo ? " [halo]" : (op.pair ? (op.ds_out >= 0 ? " [pair +1x1/2 shortcut]" : " [pair]") : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : "")));
         const void* res = op.res >= 0 ? ptr(op.res, 0) : nullptr;
         if (op.hpair)
           rc = hp_conv_launch(ctx, op.hpair, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
         else if (op.halo)
           rc = halo_conv_launch(ctx, op.halo, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
         else if (op.pair)
-          rc = pair_conv_launch(ctx, op.pair, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off));
+          rc = pair_conv_launch(ctx, op.pair, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off),
+                                op.ds_out >= 0 ? ptr(op.ds_out, op.ds_off) : nullptr);
         else if (op.impl == SPK_CONV_TCGEN05)
           rc = tc_conv_launch(ctx, op.tc, (int)n, ptr(op.in, op.in_off), res, ptr(op.out, op.out_off),
                               op.ds_out >= 0 ? ptr(op.ds_out, op.ds_off) : nullptr);

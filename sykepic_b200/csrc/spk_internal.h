@@ -156,10 +156,12 @@ int64_t halo_conv_plan_bytes(const HaloConvPlan* p);
 // conv_pair.cu (Cout >= 128: CTA pairs, tcgen05.mma.cta_group::2, each CTA stages half of the weight tile)
 struct PairConvPlan;
 bool pair_conv_supported(const ConvGeom& g);
+// w_ds / bias_ds / ldy_ds: optional fused 1x1 stride-2 shortcut of a 3x3 stride-2 convolution (as tc_conv_plan_create)
 int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
-                          const float* bias, PairConvPlan** out);
+                          const float* bias, PairConvPlan** out, const float* w_ds = nullptr, const float* bias_ds = nullptr,
+                          int ldy_ds = 0);
 void pair_conv_plan_destroy(PairConvPlan* p);
-int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y);
+int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const void* res, void* y, void* y_ds = nullptr);
 int64_t pair_conv_plan_bytes(const PairConvPlan* p);
 void pair_conv_plan_set_reverse(PairConvPlan* p, int reverse);
 // conv_hp.cu (3x3 / stride 1, Cin and Cout in {64, 128}: halo tiles on CTA pairs, filter bank resident, direct epilogue)
