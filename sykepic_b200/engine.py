@@ -438,9 +438,20 @@ class Engine:
         dview[12 * n:16 * n].view(np.int32)[:] = h
         out_bytes = n * k * 4 + (n * 4 + n if want_labels else 0)
         out = self._pinned(out_bytes)
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+        # inputs go up on their own stream: the copy of bin i+1 (~25 MB) then overlaps the kernels of bin i
+        cs = self.__dict__.get("_copy_stream")
+        if cs is None:
+            with torch.cuda.device(self.device):
+                cs = self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.device(self.device), torch.cuda.stream(cs):
             roi_dev = roi_t[:max(int(roi_len), 1)].to(self.device, non_blocking=True)
             desc_dev = desc[:16 * n].to(self.device, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(cs)
+        roi_dev.record_stream(self.stream)
+        desc_dev.record_stream(self.stream)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.stream.wait_event(up)
             start_dev = desc_dev[:8 * n].view(torch.int64)
             w_dev = desc_dev[8 * n:12 * n].view(torch.int32)
             h_dev = desc_dev[12 * n:16 * n].view(torch.int32)

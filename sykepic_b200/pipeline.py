@@ -175,6 +175,7 @@ class BinPipeline:
 
         loaders = [threading.Thread(target=loader, name=f"spk-load{k}", daemon=True) for k in range(self.n_loaders)]
         writers = [threading.Thread(target=writer, name=f"spk-write{k}", daemon=True) for k in range(self.n_writers)]
+        t_run = time.perf_counter()  # before the first file is opened
         for t in loaders + writers:
             t.start()
 
@@ -204,7 +205,6 @@ class BinPipeline:
             write_q.put(item)
 
         pending = None
-        t_run = time.perf_counter()
         try:
             for i in range(len(sample_paths)):
                 with loaded_cv:
