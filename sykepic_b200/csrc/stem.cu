@@ -272,13 +272,21 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
     for (int j = 0; j < 32; ++j) acc[j] = -INFINITY;
     int emitted = 0;
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
+    // A pooled row p is the maximum over conv rows 2p-1, 2p, 2p+1.  Even conv row 2p: acc = max(row 2p-1, row 2p), where row
+    // 2p-1 (the row that closed the previous window) is READ AGAIN from its accumulator slot, which is only released now;
+    // odd row 2p+1: acc = max(acc, row 2p+1), emit.  (Restarting the running maximum from registers instead cost a
+    // predicated move and a PLOP3 per element and row: 4 k of the 27 k instructions of a strip.)
     for (int idx = 0; idx < n_rows; ++idx) {
       const int i = c_lo + idx, slot = idx % kSlots;
+      const bool odd = (i & 1) != 0;
+      if (odd && idx == 0) continue;  // the odd row a strip starts on only seeds the first window: read with the next row
       __syncwarp();  // tcgen05.ld below is warp-collective
       mbar_wait(t_full(slot), ((uint32_t)(idx / kSlots)) & 1u);
+      const bool reread = !odd && idx > 0;  // the previous (odd) row's slot is still ours
+      if (reread && idx == 1) mbar_wait(t_full((idx - 1) % kSlots), 0);  // (row 0 of the strip was never waited for)
       tc_fence_after();
       if (tid == 160) STEM_TRACE(24 + idx);
-      const bool last_of_window = (i & 1) || (i == p.hc - 1);
+      const bool last_of_window = odd || (i == p.hc - 1);
       const int prow = i >> 1;
       const bool emit = last_of_window && prow >= p0 && prow <= p1;
       unsigned char* pool = gbase + pool_off + (emitted & 1) * kPoolBytes;
@@ -286,18 +294,35 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
       // issuing from uniform registers the first pooled row is ready before the builders finish; without this wait
       // the last conv rows of a strip were built from overwritten pixels.)
       if (emit && emitted == 0) mbar_wait(built_bar, 0);
+      const int pslot = (idx + kSlots - 1) % kSlots;
 #pragma unroll
       for (int qc = 0; qc < 2; ++qc) {  // 16 channels at a time: acc[32] + v[32] would not fit the 72-register budget
         uint32_t v[16];
         tmem_ld16(taddr0 + (uint32_t)(slot * 64 + qc * 16), v);
-        tmem_ld_wait();
-        if (qc == 1) {  // the accumulator slot is free as soon as it has been read
+        if (odd) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = fmaxf(acc[qc * 16 + j], __uint_as_float(v[j]));
+        } else if (reread) {
+          uint32_t u[16];
+          tmem_ld16(taddr0 + (uint32_t)(pslot * 64 + qc * 16), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = fmaxf(__uint_as_float(u[j]), __uint_as_float(v[j]));
+        } else {  // the first conv row of the image: the row above is padding
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = __uint_as_float(v[j]);
+        }
+        if (qc == 1) {  // accumulator slots are free as soon as they have been read: an even row's at once (together with
+                        // the odd row before it), an odd row's when the next row has re-read it -- or now, if it is the last
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty(slot));
+          if (lane == 0) {
+            if (!odd || idx == n_rows - 1) mbar_arrive(t_empty(slot));
+            if (reread) mbar_arrive(t_empty(pslot));
+          }
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = fmaxf(acc[qc * 16 + j], __uint_as_float(v[j]));
         if (emit) {
           // + bias, ReLU, bf16; row wo of the pool buffer in 16-byte chunks swizzled by (wo & 7)
 #pragma unroll
@@ -312,12 +337,6 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
             }
             *reinterpret_cast<uint4*>(pool + wo * 128 + (((4 * half + 2 * qc + c) ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-        }
-        if (last_of_window) {
-          // conv row 2p+1 is also the first row of pooled row p+1: restart the running max from it (an even last row
-          // ends the image, what it leaves in acc is never used)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[qc * 16 + j] = __uint_as_float(v[j]);
         }
       }
       if (tid == 160 && idx == 2) STEM_TRACE(56);
