@@ -517,7 +517,7 @@ int spk_net_end(spk_ctx* ctx) {
   SPK_CUDA_OK(ctx, cudaMalloc(&net->d_logits, (size_t)net->max_batch * net->classes * sizeof(float)));
   net->bytes += (int64_t)net->max_batch * net->classes * 4;
   // ---- stem fusion: conv 7x7/2 on the u8 input followed by max-pool 3x3/2 -> one tcgen05 kernel
-  if (net->precision == SPK_PRECISION_BF16 && net->ops.size() >= 2) {
+  if (net->precision != SPK_PRECISION_FP32 && net->ops.size() >= 2) {  // BF16, and FP32_TC (SplitF output)
     Op& c0 = net->ops[0];
     Op& m1 = net->ops[1];
     // is the conv output read by anything but the pool before its buffer id is written again?
@@ -742,7 +742,7 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
         (void)bp;
         rc = launch_stem_pool(ctx, (int)n, g.h, g.w, (const uint8_t*)ptr(0, 0, (size_t)g.h * g.w), op.d_stem_w, op.d_bias,
                               (__nv_bfloat16*)ptr(op.pool_out, 0, (size_t)op.hp * op.wp * op.pool_ld), g.ho,
-                              g.wo, op.hp, op.wp, op.pool_ld);
+                              g.wo, op.hp, op.wp, op.pool_ld, net->act_dtype == SPK_DTYPE_SPLIT);
         break;
       }
       case kOpMaxPool: {

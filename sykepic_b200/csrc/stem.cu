@@ -114,13 +114,18 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 #define STEM_TRACE(slot) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const StemParams p) {
+// kSplit: the output is SplitF words (bf16 hi | lo, FP32_TC precision) instead of bf16: the accumulators already carry
+// fp32 accuracy (exact bf16 pixels x bf16 hi + lo weights); only the pool buffers double (one CTA per SM then).
+template <bool kSplit>
+__global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const StemParams p) {
+  constexpr int kPoolBuf = kSplit ? 2 * kPoolBytes : kPoolBytes;  // one pooled-row buffer: 128 columns x 64 channels
+  constexpr int kPoolRow = kSplit ? 256 : 128;                    // bytes per column
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_raw + (base - raw);
   // layout: E | B | pool[2] | image strip | bias | barriers | tmem slot
-  const uint32_t e_off = 0, b_off = kEBytes, pool_off = b_off + kBBytes, img_off = pool_off + 2 * kPoolBytes;
+  const uint32_t e_off = 0, b_off = kEBytes, pool_off = b_off + kBBytes, img_off = pool_off + 2 * kPoolBuf;
   const int img_bytes = kERows * p.pitch;
   const uint32_t bias_off = (img_off + img_bytes + 15u) & ~15u;
   const uint32_t bar_off = bias_off + 64 * 4;
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
       const bool last_of_window = odd || (i == p.hc - 1);
       const int prow = i >> 1;
       const bool emit = last_of_window && prow >= p0 && prow <= p1;
-      unsigned char* pool = gbase + pool_off + (emitted & 1) * kPoolBytes;
+      unsigned char* pool = gbase + pool_off + (emitted & 1) * kPoolBuf;
       // The pool buffers alias the bf16 row buffer: wait until the builders have read all of it.  (With the MMA warp
       // issuing from uniform registers the first pooled row is ready before the builders finish; without this wait
       // the last conv rows of a strip were built from overwritten pixels.)
@@ -327,6 +332,19 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
           // + bias, ReLU, bf16; row wo of the pool buffer in 16-byte chunks swizzled by (wo & 7)
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
+            if constexpr (kSplit) {  // 8 channels = two 16-byte chunks of SplitF words
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int e = qc * 16 + c * 8 + h2 * 4 + j;
+                  o[j] = split_store(fmaxf(acc[e] + bias_sm[half * 32 + e], 0.f));
+                }
+                const int chunk = 8 * half + 4 * qc + 2 * c + h2;  // 16 chunks of 4 channels per column
+                *reinterpret_cast<uint4*>(pool + wo * kPoolRow + ((chunk ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            } else {
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -336,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
               o[j] = *reinterpret_cast<uint32_t*>(&t);
             }
             *reinterpret_cast<uint4*>(pool + wo * 128 + (((4 * half + 2 * qc + c) ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
           }
         }
       }
@@ -345,6 +364,28 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_kernel(const __grid_con
         named_bar_sync(1, kEpiThreads);  // the epilogue warps
         if (tid == 160 && idx == 2) STEM_TRACE(57);
         // horizontal max over conv columns 2pw-1, 2pw, 2pw+1 and a coalesced store of the pooled row
+        if constexpr (kSplit) {
+          // SplitF words: the maximum of three is one of them -- pick by the decoded value
+          uint32_t* yrow = reinterpret_cast<uint32_t*>(p.y) + ((size_t)image * p.hp + prow) * p.wp * p.ldy;
+          for (int o = et; o < p.wp * 16; o += kEpiThreads) {
+            const int pw = o >> 4, j = o & 15;
+            const int w1 = 2 * pw;
+            uint4 m4 = *reinterpret_cast<const uint4*>(pool + w1 * kPoolRow + ((j ^ (w1 & 7)) << 4));
+            uint32_t* mm = reinterpret_cast<uint32_t*>(&m4);
+            auto take = [&](int wn) {
+              const uint4 t4 = *reinterpret_cast<const uint4*>(pool + wn * kPoolRow + ((j ^ (wn & 7)) << 4));
+              const uint32_t* tt = reinterpret_cast<const uint32_t*>(&t4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (split_load(tt[e]) > split_load(mm[e])) mm[e] = tt[e];
+            };
+            if (w1 - 1 >= 0) take(w1 - 1);
+            if (w1 + 1 < p.wc) take(w1 + 1);
+            *reinterpret_cast<uint4*>(yrow + (size_t)pw * p.ldy + j * 4) = m4;
+          }
+          ++emitted;
+          continue;
+        }
         __nv_bfloat16* yrow = p.y + ((size_t)image * p.hp + prow) * p.wp * p.ldy;
         for (int o = et; o < p.wp * 8; o += kEpiThreads) {
           const int pw = o >> 3, j = o & 7;
@@ -415,7 +456,7 @@ int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out) {
 }
 
 int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, const uint4* w_il, const float* bias,
-                     __nv_bfloat16* y, int hc, int wc, int hp, int wp, int ldy) {
+                     __nv_bfloat16* y, int hc, int wc, int hp, int wp, int ldy, bool split) {
   if (n <= 0) return SPK_OK;
   StemParams p;
   p.x = x;
@@ -452,9 +493,12 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     cache.th = th;
     cache.tw = tw;
   }
-  const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes + (size_t)kERows * p.pitch + 32 + 64 * 4 +
+  const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes * (split ? 2 : 1) + (size_t)kERows * p.pitch + 32 + 64 * 4 +
                       8 * (kEGroups + 3 + 2 * kSlots) + 16;
-  SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (split)
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool want_trace = getenv("SPK_STEM_TRACE") != nullptr;
   static long long* d_trace = nullptr;
   static int trace_left = 3;
@@ -464,7 +508,10 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     cudaMemsetAsync(d_trace, 0, 16 * 64 * sizeof(long long), ctx->stream);
     p.trace = d_trace;
   }
-  SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
+  if (split)
+    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<true>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
+  else
+    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<false>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   SPK_LAUNCH_CHECK(ctx);
   if (p.trace) {
     --trace_left;
