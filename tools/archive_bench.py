@@ -84,7 +84,8 @@ def main():
             "wall_s_incl_engine_construction": wall, "value_incl_engine_construction": float(t[1]) / wall,
             "stage_seconds_rank0": {k: round(st[k], 4) for k in ("load_s", "gpu_wait_s", "write_s")}, "roi_gb": float(t[2]) / 1e9, "csv_gb": float(t[3]) / 1e9,
             "config": {"workload": f"{args.arch} 3x224x224 {args.precision}, synthetic IFCB bins on {base or 'tmp'}, "
-                                   f"batch {args.batch_size}, probability.main (read -> GPU -> %.5f CSV files)"},
+                                   f"-b {args.batch_size} (launches of max(b, SYKEPIC_MIN_BATCH = {os.environ.get('SYKEPIC_MIN_BATCH', '1024')}) ROIs), "
+                                   f"probability.main (read -> GPU -> %.5f CSV files)"},
             "host_cpus": os.cpu_count()}), flush=True)
     if world > 1:
         dist.barrier()
