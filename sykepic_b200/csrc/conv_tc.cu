@@ -55,6 +55,11 @@ struct alignas(64) TcParams {
   int taps, kchunks, cin_pad;
   int total_tiles;
   int reverse;  // walk the tiles last-to-first (see conv_hp.cu)
+  // kModePre: y = conv(relu(x * pre_scale[c] + pre_shift[c])): DenseNet's pre-activation BatchNorm + ReLU applied to the A
+  // tiles in shared memory (every consumer of a concatenation has its own BatchNorm, so it cannot be folded into a producer)
+  const float* pre_scale;
+  const float* pre_shift;
+  int pre_c, pre_relu;
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
 
@@ -186,27 +191,32 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // twice the channels, K index 2c = hi_c, 2c + 1 = lo_c.  Every k block is multiplied by TWO weight tiles into the same
 // accumulator: [w_hi, w_hi] (gives x_hi*w_hi + x_lo*w_hi) and [w_lo, w_lo] (x_hi*w_lo + x_lo*w_lo): the full 16-bit x
 // 16-bit product with fp32 accumulation (torch emulation of ResNet-18: |dp| <= 5e-6, experiments/emul_bf16x3_split.py).
-constexpr int kModePlain = 0, kModeDs = 1, kModeSplit = 2;
+constexpr int kModePlain = 0, kModeDs = 1, kModeSplit = 2, kModePre = 3;
+constexpr int kPreWarps = 8;                      // kModePre: transform warps 6..13
+constexpr int kThreadsPre = kThreads + 32 * kPreWarps;
+constexpr int kPreTable = 2 * 1024 * 4;           // scale | shift for up to 1024 input channels
 
 template <int BN, int MODE = 0>
 struct Cfg {
   static constexpr bool DS = MODE == kModeDs;
   static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes * (MODE != 0 ? 2 : 1);
-  static constexpr int kStages = MODE != 0 ? (BN >= 128 ? 4 : 6) : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));
-  static constexpr int kAccCols = MODE != 0 ? 2 * BN : BN;     // main accumulator (+ the downsample's / the lo pass's beside it)
+  static constexpr bool kTwoB = MODE == kModeDs || MODE == kModeSplit;  // two weight tiles per stage, two accumulators
+  static constexpr int kStageBytes = kABytes + kBBytes * (kTwoB ? 2 : 1);
+  static constexpr int kStages = kTwoB ? (BN >= 128 ? 4 : 6) : (BN >= 256 ? 4 : (BN >= 128 ? 6 : 8));
+  static constexpr int kAccCols = kTwoB ? 2 * BN : BN;         // main accumulator (+ the downsample's / the lo pass's beside it)
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;  // double-buffered (power of two)
-  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (MODE == kModePre ? kPreTable : 0);
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10),
   // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
   static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 };
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   using C = Cfg<BN, MODE>;
   constexpr bool DS = MODE == kModeDs;
   constexpr bool SPLIT = MODE == kModeSplit;
+  constexpr bool PRE = MODE == kModePre;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -218,6 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + C::kStages * C::kStageBytes + 8 * (2 * C::kStages + 4));
+  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + 5 + s); };  // kModePre: the A tile has been transformed
+  float* pre_tab = reinterpret_cast<float*>(gen_base + C::kStages * C::kStageBytes + 256);  // kModePre: scale[1024] | shift[1024]
+  (void)ready_bar;
+  (void)pre_tab;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -235,7 +249,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&p.map_b);
     tma_prefetch_desc(&p.map_a[0]);
-    if (MODE != 0) tma_prefetch_desc(&p.map_b2);
+    if (DS || SPLIT) tma_prefetch_desc(&p.map_b2);
+    if (PRE)
+      for (int s = 0; s < C::kStages; ++s) mbar_init(ready_bar(s), kPreWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (PRE) {  // the BatchNorm table, zero beyond the real channels (TMA zero-fills those and they must stay zero)
+    for (int i = threadIdx.x; i < 2 * 1024; i += blockDim.x) {
+      const int c = i & 1023;
+      pre_tab[i] = c < p.pre_c ? __ldg((i < 1024 ? p.pre_scale : p.pre_shift) + c) : 0.f;
+    }
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)),
@@ -295,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::kAccCols);
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(PRE ? ready_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * C::kStageBytes;
           const uint64_t a_desc = smem_desc_sw128(sa);
@@ -338,7 +361,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
-  } else {
+  } else if (PRE && warp >= 6) {
+    // ===== kModePre transform: 8 warps, thread -> (pixel row, four of its eight 16-byte channel chunks).  SWIZZLE_128B
+    // puts logical chunk j of row r at physical chunk j ^ (r & 7).  Same arithmetic as the stand-alone affine_relu kernel
+    // (fp32 fma, ReLU, round to bf16), so the fused result is bit-identical to the unfused one. =====
+    const int tt = threadIdx.x - kThreads;
+    const int r = tt & 127, jh = (tt >> 7) * 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int c0 = (kb % p.kchunks) * kBK;
+        mbar_wait(full_bar(stage), phase);
+        unsigned char* row = gen_base + stage * C::kStageBytes + r * 128;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = jh + jj;
+          uint4* cp = reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4));
+          uint4 q = *cp;
+          __nv_bfloat162* b2 = reinterpret_cast<__nv_bfloat162*>(&q);
+          const float* sc = pre_tab + c0 + 8 * j;
+          const float* sh = pre_tab + 1024 + c0 + 8 * j;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(b2[e]);
+            float a = fmaf(f.x, sc[2 * e], sh[2 * e]), b = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+            if (p.pre_relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            b2[e] = __floats2bfloat162_rn(a, b);
+          }
+          *cp = q;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(stage));
+        if (++stage == C::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 6) {
     // ===== epilogue: 4 warps, warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;  // pixel of the tile == TMEM lane
@@ -504,6 +569,7 @@ struct TcConvPlan {
   int bn = 0;
   bool ds = false;
   bool split = false;
+  bool pre = false;
   TcParams prm;
   __nv_bfloat16* d_w = nullptr;
   __nv_bfloat16* d_w2 = nullptr;
@@ -557,6 +623,25 @@ bool tc_conv_split_supported(const ConvGeom& g) {
   v.ldx = 2 * g.ldx;
   if (g.cin % 4 != 0 || g.ldy % 4 != 0 || g.ldres % 4 != 0) return false;  // 16-byte SplitF accesses in the epilogue
   return tc_conv_supported(v) && pick_bn(g.cout) != 0;
+}
+
+int tc_conv_plan_set_prologue(spk_ctx* ctx, TcConvPlan* p, const float* d_scale, const float* d_shift, int channels, int relu) {
+  if (!p || p->ds || p->split) return fail(ctx, SPK_ERR_STATE, "tcgen05 convolution: prologue on a fused / split plan");
+  if (channels > 1024 || channels > p->g.cin) return fail(ctx, SPK_ERR_UNSUPPORTED, "tcgen05 convolution: prologue over %d channels", channels);
+  p->pre = true;
+  p->prm.pre_scale = d_scale;
+  p->prm.pre_shift = d_shift;
+  p->prm.pre_c = channels;
+  p->prm.pre_relu = relu;
+  cudaError_t ea = cudaSuccess;
+  switch (p->bn) {
+    case 256: ea = cudaFuncSetAttribute(conv_tc_kernel<256, kModePre>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<256, kModePre>::kSmem); break;
+    case 128: ea = cudaFuncSetAttribute(conv_tc_kernel<128, kModePre>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<128, kModePre>::kSmem); break;
+    case 64: ea = cudaFuncSetAttribute(conv_tc_kernel<64, kModePre>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64, kModePre>::kSmem); break;
+    case 32: ea = cudaFuncSetAttribute(conv_tc_kernel<32, kModePre>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<32, kModePre>::kSmem); break;
+  }
+  if (ea != cudaSuccess) return fail(ctx, SPK_ERR_CUDA, "tcgen05 convolution: cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
+  return SPK_OK;
 }
 
 int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, const float* d_bias, TcConvPlan** out,
@@ -766,7 +851,7 @@ template <int BN, int MODE = 0>
 static int launch_bn(spk_ctx* ctx, const TcParams& prm) {
   using C = Cfg<BN, MODE>;
   const int grid = std::min(prm.total_tiles, ctx->sm_count);
-  SPK_CUDA_OK(ctx, tc::launch_pdl(conv_tc_kernel<BN, MODE>, dim3(grid), dim3(kThreads), C::kSmem, ctx->stream, prm));
+  SPK_CUDA_OK(ctx, tc::launch_pdl(conv_tc_kernel<BN, MODE>, dim3(grid), dim3(MODE == kModePre ? kThreadsPre : kThreads), C::kSmem, ctx->stream, prm));
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;
 }
@@ -786,6 +871,12 @@ int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void
   if (p->ds && !y_ds) return fail(ctx, SPK_ERR_INVALID, "tcgen05 convolution: fused downsample without an output");
   prm.tiles_img = (n + prm.nb - 1) / prm.nb;
   prm.total_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img * prm.tiles_n;
+  if (p->pre) switch (p->bn) {
+      case 256: return launch_bn<256, kModePre>(ctx, prm);
+      case 128: return launch_bn<128, kModePre>(ctx, prm);
+      case 64: return launch_bn<64, kModePre>(ctx, prm);
+      case 32: return launch_bn<32, kModePre>(ctx, prm);
+    }
   if (p->split) return p->bn == 128 ? launch_bn<128, kModeSplit>(ctx, prm) : p->bn == 64 ? launch_bn<64, kModeSplit>(ctx, prm) : launch_bn<32, kModeSplit>(ctx, prm);
   if (p->ds) return p->bn == 128 ? launch_bn<128, kModeDs>(ctx, prm) : launch_bn<64, kModeDs>(ctx, prm);
   switch (p->bn) {

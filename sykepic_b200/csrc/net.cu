@@ -36,7 +36,9 @@ struct Op {
   int impl = SPK_CONV_SIMT;
   float* d_w = nullptr;    // SIMT: [K][Cout] fp32
   float* d_bias = nullptr; // conv: folded bias [Cout]; bn_relu: shift [C]
-  float* d_scale = nullptr;  // bn_relu: scale [C]
+  float* d_scale = nullptr;  // bn_relu: scale [C]; conv with a fused pre-activation: its scale
+  float* d_pre_shift = nullptr;  // conv with a fused pre-activation (DenseNet BN + ReLU applied to the A tiles): shift
+  int pre_c = 0, pre_relu = 0;
   TcConvPlan* tc = nullptr;
   HaloConvPlan* halo = nullptr;
   HpConvPlan* hpair = nullptr;
@@ -77,6 +79,7 @@ static void net_free(Net* net) {
     if (op.d_w) cudaFree(op.d_w);
     if (op.d_bias) cudaFree(op.d_bias);
     if (op.d_scale) cudaFree(op.d_scale);
+    if (op.d_pre_shift) cudaFree(op.d_pre_shift);
     if (op.d_bias_ds) cudaFree(op.d_bias_ds);
     if (op.d_stem_w) cudaFree(op.d_stem_w);
     if (op.tc) tc_conv_plan_destroy(op.tc);
@@ -567,6 +570,46 @@ int spk_net_end(spk_ctx* ctx) {
       a.kind = kOpNop;
     }
   }
+  // ---- pre-activation fusion (DenseNet): bn_relu(concat[:, :c]) -> 1x1 convolution becomes one launch; the BatchNorm +
+  // ReLU is applied to the convolution's A tiles in shared memory (conv_tc.cu, kModePre).  Only unpadded convolutions:
+  // a padding pixel must stay 0, not relu(shift).
+  if (net->precision == SPK_PRECISION_BF16 && !getenv("SPK_NO_PRE_FUSION")) {
+    for (size_t i = 0; i + 1 < net->ops.size(); ++i) {
+      Op& a = net->ops[i];      // bn_relu
+      Op& b = net->ops[i + 1];  // its only consumer
+      if (a.kind != kOpBnRelu || b.kind != kOpConv || b.in != a.out || b.in_off != 0 || b.pad != 0 || b.g.pad != 0) continue;
+      if (b.impl == SPK_CONV_SIMT || b.impl == SPK_CONV_TCGEN05_TAPS || b.g.cin != a.channels || a.channels > 1024) continue;
+      if (net->bufs[(size_t)a.in].dtype != SPK_DTYPE_BF16) continue;
+      bool other_reader = false, overwritten = false;
+      for (size_t j = i + 2; j < net->ops.size(); ++j) {
+        const Op& o = net->ops[j];
+        if (o.kind == kOpNop) continue;
+        if (o.in == a.out || o.res == a.out) {
+          other_reader = true;
+          break;
+        }
+        if (o.out == a.out || o.pool_out == a.out || o.ds_out == a.out) {  // recycled id: overwritten first
+          overwritten = true;
+          break;
+        }
+      }
+      if (!overwritten && net->head_in == a.out) other_reader = true;  // still live when the head reads it
+      if (other_reader) continue;
+      ConvGeom g = b.g;
+      g.ldx = a.g.ldx;
+      g.n = net->max_batch;
+      if (!tc_conv_supported(g)) continue;
+      b.in = a.in;
+      b.g.ldx = a.g.ldx;
+      b.d_scale = a.d_scale;
+      b.d_pre_shift = a.d_bias;
+      b.pre_c = a.channels;
+      b.pre_relu = a.relu;
+      a.d_scale = nullptr;
+      a.d_bias = nullptr;
+      a.kind = kOpNop;
+    }
+  }
   for (auto& op : net->ops) {
     if (op.kind != kOpConv) continue;
     const ConvGeom& g = op.g;
@@ -589,7 +632,13 @@ int spk_net_end(spk_ctx* ctx) {
     if (impl == SPK_CONV_TCGEN05) {
       ConvGeom gm = g;
       gm.n = net->max_batch;
-      if (net->precision != SPK_PRECISION_BF16) {
+      if (op.pre_c > 0) {
+        rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc);
+        if (rc) return rc;
+        rc = tc_conv_plan_set_prologue(ctx, op.tc, op.d_scale, op.d_pre_shift, op.pre_c, op.pre_relu);
+        if (rc) return rc;
+        net->bytes += tc_conv_plan_bytes(op.tc);
+      } else if (net->precision != SPK_PRECISION_BF16) {
         rc = tc_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.tc, nullptr, nullptr, 0, true);
         if (rc) return rc;
         net->bytes += tc_conv_plan_bytes(op.tc);
@@ -713,7 +762,7 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
                        (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * ((op.res >= 0 ? 2 : 1) + ds_taps) +
                            (double)g.cout * (g.kh * g.kw + ds_taps) * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
                        "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
-                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.hpair ? " [halo pair]" : op.halo ? " [halo]" : (op.pair ? (op.ds_out >= 0 ? " [pair +1x1/2 shortcut]" : " [pair]") : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : "")));
+                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.hpair ? " [halo pair]" : op.halo ? " [halo]" : (op.pair ? (op.ds_out >= 0 ? " [pair +1x1/2 shortcut]" : " [pair]") : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : (op.pre_c > 0 ? " [bn+relu on A]" : ""))));
         const size_t img_in = (size_t)g.h * g.w * g.ldx, img_out = (size_t)g.ho * g.wo * g.ldy;
         const void* res = op.res >= 0 ? ptr(op.res, 0, (size_t)g.ho * g.wo * g.ldres) : nullptr;
         if (op.hpair)

@@ -140,6 +140,8 @@ bool tc_conv_split_supported(const ConvGeom& g);
 int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
                         const float* bias, TcConvPlan** out, const float* w_ds = nullptr, const float* bias_ds = nullptr,
                         int ldy_ds = 0, bool split = false);
+// y = conv(relu(x * scale[c] + shift[c])) over the first `channels` input channels (device arrays of that length)
+int tc_conv_plan_set_prologue(spk_ctx* ctx, TcConvPlan* p, const float* d_scale, const float* d_shift, int channels, int relu);
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void* res, void* y, void* y_ds = nullptr);
 int64_t tc_conv_plan_bytes(const TcConvPlan* p);
