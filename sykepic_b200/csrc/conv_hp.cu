@@ -80,7 +80,8 @@ template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3_hp_kernel(const __grid_constant__ HpParams p) {
   constexpr int kBHalf = (BN / 2) * 128;  // bytes of this CTA's half of one (chunk, tap) weight tile
   constexpr int kTmemCols = 2 * BN;       // double-buffered accumulator
-  constexpr int kSlabs = BN / 64;
+  constexpr int kSlabs = BN >= 64 ? BN / 64 : 1;  // 64-channel slabs (BN = 32: one half slab, taken by the `half == 0` warps)
+  constexpr int kTmemAlloc = kTmemCols < 32 ? 32 : kTmemCols;
   constexpr uint32_t kIdesc = idesc_bf16(256, BN);
 
   extern __shared__ unsigned char smem_raw[];
@@ -121,7 +122,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
     tma_prefetch_desc(&p.map_x);
     tma_prefetch_desc(&p.map_w);
   }
-  if (warp == 1) tmem2_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
+  if (warp == 1) tmem2_alloc(smem_u32((const void*)tmem_slot), kTmemAlloc);
   for (int i = threadIdx.x; i < p.cout; i += kThreads) bias_sm[i] = __ldg(p.bias + i);
   tc_fence_before();
   cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals them
@@ -235,6 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
     const int j = q * 32 + lane;  // TMEM lane == linear halo-pitch pixel of this CTA's tile
     const int jr = j / p.pitch, jc = j - jr * p.pitch;
     const uint32_t t_empty_leader = mapa_rank(t_empty(0), 0);
+    const bool works = BN >= 64 || half == 0;  // BN = 32: the second warp of a lane quarter only keeps the barrier counts
     pdl_wait();  // residual reads and output writes wait for the previous kernel
     int acc = 0;
     uint32_t accph = 0;
@@ -243,7 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
     auto res_load = [&](int u, U8 (&r)[kSlabs][2]) {
       int img, h0;
       const bool tile_ok = tile_coords(u, img, h0);
-      if (tile_ok && (jc < p.w) && (jr < p.hb) && (h0 + jr < p.h)) {
+      if (works && tile_ok && (jc < p.w) && (jr < p.hb) && (h0 + jr < p.h)) {
         const __nv_bfloat16* rp = p.res + (((long long)img * p.h + (h0 + jr)) * p.w + jc) * p.ldres + half * 32;
 #pragma unroll
         for (int slab = 0; slab < kSlabs; ++slab)
@@ -262,7 +264,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
     for (int u = cluster_id; u < p.units; u += n_clusters) {
       int img, h0;
       const bool tile_ok = tile_coords(u, img, h0);
-      const bool inside = tile_ok && (jc < p.w) && (jr < p.hb) && (h0 + jr < p.h);
+      const bool inside = works && tile_ok && (jc < p.w) && (jr < p.hb) && (h0 + jr < p.h);
       const long long pix = ((long long)img * p.h + (h0 + jr)) * p.w + jc;
       U8 rv[kSlabs][2];
 #pragma unroll
@@ -274,9 +276,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
       tc_fence_after();
 #pragma unroll
       for (int slab = 0; slab < kSlabs; ++slab) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * 64 + half * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + slab * 64 + (BN >= 64 ? half * 32 : 0));
         uint32_t v[32];
-        tmem_ld32(taddr, v);
+        tmem_ld32(taddr, v);  // (BN = 32: both warps of a quarter read the same 32 columns; only one of them stores)
         tmem_ld_wait();
         if (slab == kSlabs - 1) {  // accumulator buffer drained: tell the leader's MMA thread
           tc_fence_before();
@@ -330,7 +332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
   cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still read this CTA's shared memory
   if (warp == 1) {
     tc_fence_after();
-    tmem2_dealloc(tmem_base, kTmemCols);
+    tmem2_dealloc(tmem_base, kTmemAlloc);
   }
 }
 
@@ -375,9 +377,17 @@ struct HpConvPlan {
 bool hp_conv_supported(const ConvGeom& g) {
   static const bool off = getenv("SPK_NO_HP") != nullptr;  // A/B switch
   if (off) return false;
-  if (!halo_conv_supported(g)) return false;
-  if ((g.cout != 64 && g.cout != 128) || (g.cin != 64 && g.cin != 128)) return false;
-  if (g.ldy % 16 != 0 || g.ldres % 16 != 0) return false;  // 32-byte epilogue accesses
+  if (g.kh != 3 || g.kw != 3 || g.stride != 1 || g.pad != 1) return false;
+  if ((g.cout != 32 && g.cout != 64 && g.cout != 128) || (g.cin != 64 && g.cin != 128)) return false;
+  if (g.ldx % 8 != 0 || g.ldy % 16 != 0 || g.ldres % 16 != 0) return false;  // TMA rows; 32-byte epilogue accesses
+  if (g.w + 2 > 128 || g.ho != g.h || g.wo != g.w) return false;
+  int hb;
+  halo_rows(g, &hb);
+  if (hb < 1) return false;
+  const int tiles_h = (g.h + hb - 1) / hb;
+  const double eff = (double)(g.w * hb) / 128.0 * (double)g.h / (double)(tiles_h * hb);
+  if (eff < 0.75) return false;  // share of the 128 MMA rows that are real output pixels (14x14 maps: 0.77)
+  if (encode_fn() == nullptr) return false;
   int a_stage;
   size_t smem;
   return plan_smem(g, &a_stage, &smem) > 0;
@@ -428,8 +438,9 @@ int hp_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
       return fail(ctx, SPK_ERR_CUDA, "halo-pair convolution: cuTensorMapEncodeTiled(W) failed: %d", (int)r);
     }
   }
-  cudaError_t ea = g.cout == 128 ? cudaFuncSetAttribute(conv3x3_hp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
-                                 : cudaFuncSetAttribute(conv3x3_hp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+  cudaError_t ea = g.cout == 128  ? cudaFuncSetAttribute(conv3x3_hp_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
+                   : g.cout == 64 ? cudaFuncSetAttribute(conv3x3_hp_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax)
+                                  : cudaFuncSetAttribute(conv3x3_hp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
   if (ea != cudaSuccess) {
     hp_conv_plan_destroy(p);
     return fail(ctx, SPK_ERR_CUDA, "halo-pair convolution: cudaFuncSetAttribute: %s", cudaGetErrorString(ea));
@@ -480,6 +491,8 @@ int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void
   }
   if (g.cout == 128)
     SPK_CUDA_OK(ctx, launch_pdl(conv3x3_hp_kernel<128>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
+  else if (g.cout == 32)
+    SPK_CUDA_OK(ctx, launch_pdl(conv3x3_hp_kernel<32>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   else
     SPK_CUDA_OK(ctx, launch_pdl(conv3x3_hp_kernel<64>, dim3(2 * clusters), dim3(kThreads), p->smem, ctx->stream, prm));
   SPK_LAUNCH_CHECK(ctx);

@@ -90,6 +90,10 @@ GEOMS = [
     (57, 3, 64, 64, 3, 1, 1, True, True),       # resident weights, H not a multiple of the tile rows (TMA store clips)
     (30, 3, 64, 128, 3, 1, 1, True, False),     # Cin 64 -> Cout 128, 4-row tiles with a 2-row remainder
     (28, 2, 64, 192, 3, 1, 1, True, True),      # three N tiles of 64
+    (28, 3, 128, 32, 3, 1, 1, False, False),    # DenseNet growth convolution: halo-pair kernel with N = 32
+    (56, 3, 128, 32, 3, 1, 1, True, False),     # ... on 56x56 maps (2-row tiles, odd tile count)
+    (14, 5, 128, 32, 3, 1, 1, False, False),    # ... on 14x14 maps (8-row tiles, the second one clipped)
+    (14, 6, 128, 128, 3, 1, 1, True, True),     # 14x14 with residual through the halo-pair kernel
 ]
 HALO_GEOMS = [0, 1, 10, 12, 2, 4, 5, 9]  # halo / pair geometries also run through the tap-per-TMA kernel (SPK_CONV_TCGEN05_TAPS)
 
