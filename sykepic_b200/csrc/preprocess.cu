@@ -850,7 +850,7 @@ extern "C" int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t ro
     preprocess_big_kernel<<<kBigClusters * kBigSlabs, kThreads, kHBytes, ctx->stream2>>>(pb);
     SPK_LAUNCH_CHECK(ctx);
     SPK_CUDA_OK(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
-    p.slabs = n <= 1024 ? 4 : n <= 2048 ? 2 : 1;  // warps per ROI
+    p.slabs = n <= 2048 ? 4 : n <= 8192 ? 2 : 1;  // warps per ROI (fills the partial last wave of a bin-sized launch)
     const long long items = n * p.slabs;
     preprocess_u8_kernel<<<(unsigned)((items + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, (long long)n);
     SPK_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
