@@ -147,30 +147,73 @@ def main(
         if len(devices) <= 1:
             return run_on(devices[0], sample_paths)
 
-        # ---- bins sharded over the GPUs of the box; host-side merge = union of the per-GPU sets
+        # ---- bins sharded over the GPUs of the box; host-side merge = union of the per-GPU sets.
+        # One PROCESS per GPU: with one thread per GPU in a single interpreter the host stages contend for the GIL
+        # (measured on 8 GPUs, 128 bins: 0.52 M ROI/s with threads, 1.09 M with processes).
         shards = shard.assign_bins(sample_paths, len(devices))
-        results = [set() for _ in devices]
-        errors = []
+        # (spawning costs ~4 s of start-up per job: threads for small jobs and up to 2 GPUs)
+        mode = os.environ.get("SYKEPIC_MULTI") or ("processes" if len(devices) > 2 and len(sample_paths) >= 8 * len(devices) else "threads")
+        if mode == "threads":
+            results = [set() for _ in devices]
+            errors = []
 
-        def worker(i):
-            try:
-                results[i] = run_on(devices[i], shards[i])
-            except Exception as e:  # engine construction failed: report, do not hang the others
-                errors.append(e)
+            def worker(i):
+                try:
+                    results[i] = run_on(devices[i], shards[i])
+                except Exception as e:  # engine construction failed: report, do not hang the others
+                    errors.append(e)
 
-        threads = [threading.Thread(target=worker, args=(i,), name=f"spk-gpu{devices[i]}") for i in range(len(devices))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        for r in results:
-            samples_processed |= r
+            threads = [threading.Thread(target=worker, args=(i,), name=f"spk-gpu{devices[i]}") for i in range(len(devices))]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+            for r in results:
+                samples_processed |= r
+            return samples_processed
+        import multiprocessing as mp
+
+        ctx = mp.get_context("spawn")
+        queue = ctx.Queue()
+        procs = [ctx.Process(target=_shard_process, name=f"spk-gpu{dev}",
+                             args=(dev, [str(p) for p in shards[i]], str(model_dir), str(out_dir), batch_size, num_workers, force, precision, queue))
+                 for i, dev in enumerate(devices)]
+        for pr in procs:
+            pr.start()
+        failures = []
+        for _ in procs:
+            dev, done, err, stats = queue.get()
+            if err:
+                failures.append(f"GPU {dev}: {err}")
+            samples_processed |= set(done)
+            if stats:
+                from .. import pipeline
+
+                pipeline.LAST_STATS.append(stats)
+            if bar is not None:
+                bar.update(len(done))
+        for pr in procs:
+            pr.join()
+        if failures:
+            raise RuntimeError("; ".join(failures))
         return samples_processed
     finally:
         if bar is not None:
             bar.close()
+
+
+def _shard_process(dev, paths, model_dir, out_dir, batch_size, num_workers, force, precision, queue):
+    """Worker process of one GPU: its shard of the bins through `main` on that device; reports the processed set."""
+    try:
+        from .. import pipeline
+
+        done = main([Path(p) for p in paths], model_dir, out_dir, batch_size, num_workers, force, progress_bar=False,
+                    precision=precision, devices=[dev])
+        queue.put((dev, sorted(done), None, pipeline.LAST_STATS[-1] if pipeline.LAST_STATS else None))
+    except Exception as e:  # engine construction / CUDA failure: the parent raises after the others finish
+        queue.put((dev, [], repr(e), None))
 
 
 class _LockedBar:

@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--batch-size", type=int, default=256)
     ap.add_argument("--root", default=None, help="work directory (default: a temp dir on /dev/shm if present)")
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--devices", type=int, default=0,
+                    help="single process, one host thread + pipeline per GPU for the first N GPUs (what `sykepic prob --gpus N` does); "
+                         "default: one process per GPU under torchrun")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -39,6 +42,8 @@ def main():
     from sykepic_b200.compute import probability
 
     rank, world, local = shard.rank_world()
+    if args.devices > 0:
+        return threads_mode(args)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -90,6 +95,43 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not args.keep:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def threads_mode(args):
+    """`probability.main(devices=[0..N-1])` in ONE process: bins sharded by .roi size, one engine + pipeline per GPU thread."""
+    import torch
+
+    from sykepic_b200 import pipeline, synth
+    from sykepic_b200.compute import probability
+
+    base = args.root or ("/dev/shm" if Path("/dev/shm").is_dir() else None)
+    root = Path(tempfile.mkdtemp(prefix="spk_archive_thr_", dir=base))
+    raw, out = root / "raw", root / "out"
+    mdir = synth.write_model_dir(root / "model", arch=args.arch, t=224, head=(256, 128), seed=0, border="mode",
+                                 imagenet_normalization=False, randomize_bn=True, logit_gain=8.0)
+    n_rois = 0
+    for i in range(args.bins):
+        b = synth.synth_bin(1000 + i)
+        synth.write_bin(raw, synth.bin_name(i), b)
+        n_rois += int((b["w"] > 0).sum())
+    paths = sorted(p.with_suffix("") for p in raw.glob("*.roi"))
+    devs = list(range(args.devices))
+    probability.main(paths[:len(devs)], mdir, root / "warm", batch_size=args.batch_size, progress_bar=False, precision=args.precision, devices=devs)
+    for d in devs:
+        torch.cuda.synchronize(d)
+    n0 = len(pipeline.LAST_STATS)
+    t0 = time.perf_counter()
+    done = probability.main(paths, mdir, out, batch_size=args.batch_size, progress_bar=False, precision=args.precision, devices=devs)
+    dt = time.perf_counter() - t0
+    assert len(done) == len(paths), (len(done), len(paths))
+    runs = pipeline.LAST_STATS[n0:]
+    pipe_s = max(r["run_s"] for r in runs)
+    print(json.dumps({
+        "metric": "ifcb_rois_per_s_archive_e2e", "value": n_rois / pipe_s, "unit": "ROIs/s", "n_gpus": len(devs), "mode": "probability.main(devices=N): " + (os.environ.get("SYKEPIC_MULTI") or "auto (threads up to 2 GPUs, else a process per GPU)"),
+        "bins": len(paths), "rois": n_rois, "first_open_to_last_csv_s": pipe_s, "wall_s_incl_engine_construction": dt,
+        "value_incl_engine_construction": n_rois / dt, "bins_per_gpu": [r["bins"] for r in runs], "host_cpus": os.cpu_count()}), flush=True)
     if not args.keep:
         shutil.rmtree(root, ignore_errors=True)
 
