@@ -170,10 +170,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA): the whole warp runs the loop with warp-uniform values, one elected lane issues.
-    // A satisfied mbarrier wait + tcgen05 fence still costs ~150-200 cycles of this warp (trace: 385 cycles per
-    // 1150-cycle unit at N = 64), during which the MMA queue runs dry.  The waits for the NEXT chunk (its halo stage,
-    // and the accumulator buffer when it starts a unit) are therefore done after the FIFTH tap of the current chunk,
-    // while four taps' worth of MMAs are still queued. =====
+    // A satisfied mbarrier wait + tcgen05 fence still costs ~150-200 cycles of this warp, during which the MMA queue
+    // would run dry.  The waits for the NEXT chunk (its halo stage, and the accumulator buffer when it starts a unit)
+    // are therefore done after the FIFTH tap of the current chunk, while four taps' worth of MMAs are still queued.
+    // Trace (SPK_HP_TRACE, 64 -> 64 at 56x56): 20 MMAs issue in ~540 cycles, t_empty ~220, a_full ~160, fence ~90,
+    // 16 MMAs ~450: ~1500 cycles per unit -- which is this shape's shared-memory bound, not the waits: each K=16 MMA
+    // reads 128 x 32 B of A and 32 x 32 B of B per CTA (5 KB, 40 cycles at 128 B/clk), 36 of them = 1440 cycles.
+    // With a residual the t_empty wait grows to 900-1400 cycles (the epilogue, i.e. HBM, is the limiter there; an L2
+    // prefetch of the residual two units ahead changed nothing). =====
     if (leader) {
       mbar_wait(b_full, 0);
       int as = 0, acc = 0, tr = 0;
@@ -181,9 +185,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
       const bool tracing = p.trace != nullptr && cluster_id == 3 && lane == 0;
       // flat sequence of chunks: chunk c of unit u; `ready` = the barriers of the chunk about to be issued have been waited for
       auto wait_chunk = [&](int ch, int as_, uint32_t aph_, int acc_, uint32_t accph_) {
+        if (tracing && tr < 250) p.trace[tr++] = clock64();
         if (ch == 0) mbar_wait_cluster(t_empty(acc_), accph_ ^ 1u);  // both CTAs have drained this accumulator buffer
+        if (tracing && tr < 250) p.trace[tr++] = clock64();
         mbar_wait(a_full(as_), aph_);
+        if (tracing && tr < 250) p.trace[tr++] = clock64();
         tc_fence_after();
+        if (tracing && tr < 250) p.trace[tr++] = clock64();
       };
       if (cluster_id < p.units) wait_chunk(0, as, aph, acc, accph);
       for (int u = cluster_id; u < p.units; u += n_clusters) {
@@ -356,7 +364,8 @@ int plan_smem(const ConvGeom& g, int* a_stage_out, size_t* smem_out) {
   const size_t fixed = 1024 /*alignment*/ + (size_t)g.cout * 4 + 16 + 8 * (2 * kMaxRing + 6) + 16;
   if (size_b + fixed + (size_t)a_stage > kSmemMax) return 0;
   int na = (int)std::min<size_t>(kMaxRing, (kSmemMax - fixed - size_b) / (size_t)a_stage);
-  if (na > 3 * kchunks) na = 3 * kchunks;
+  if (na > 3 * kchunks) na = 3 * kchunks;  // (6 stages measured the same as 3: the a_full wait in the trace is the ~160-cycle
+                                           // cost of a satisfied wait, not TMA latency)
   if (na < kchunks + 1 && na < 3) return 0;  // the next tile's first chunk must be loadable while this tile computes
   *a_stage_out = a_stage;
   *smem_out = fixed + size_b + (size_t)na * a_stage;
@@ -501,7 +510,7 @@ int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void
     long long h[256];
     cudaStreamSynchronize(ctx->stream);
     cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "hp trace cin=%d cout=%d w=%d units=%d na=%d res=%d (cycles since the first stamp; per unit: start, t_empty, a_full per chunk):\n ",
+    fprintf(stderr, "hp trace cin=%d cout=%d w=%d units=%d na=%d res=%d (cycles since the first stamp; per unit: start, then mid-chunk: before t_empty, after, after a_full, after fence):\n ",
             g.cin, g.cout, g.w, prm.units, prm.na, prm.has_res);
     for (int i = 0; i < 250 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
     fprintf(stderr, "\n");
