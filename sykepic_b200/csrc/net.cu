@@ -535,7 +535,7 @@ int spk_net_end(spk_ctx* ctx) {
     if (c0.kind == kOpConv && c0.in == 0 && net->bufs[0].dtype == SPK_DTYPE_U8 && c0.impl != SPK_CONV_SIMT &&
         m1.kind == kOpMaxPool && m1.in == c0.out && c0.res < 0 && c0.out_off == 0 && net->head_in != c0.out &&
         stem_pool_supported(c0.g, m1.k, m1.stride, m1.pad) && (m1.g.ldy % 8) == 0 && !other_reader) {
-      rc = stem_pool_pack_weights(ctx, c0.w_host.data(), &c0.d_stem_w);
+      rc = stem_pool_pack_weights(ctx, c0.w_host.data(), &c0.d_stem_w, net->act_dtype == SPK_DTYPE_SPLIT);
       if (rc) return rc;
       net->bytes += 16384;
       rc = upload(ctx, c0.b_host.data(), c0.b_host.size(), &c0.d_bias);

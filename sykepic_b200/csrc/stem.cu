@@ -28,6 +28,11 @@
 //              memory, coalesced 16-byte stores.
 // The 112x112x64 conv output (411 MB per 256 images in bf16) never exists in HBM.
 #include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
 
 #include <cstdlib>
 #include <cstring>
@@ -76,6 +81,7 @@ __device__ __forceinline__ uint64_t smem_desc_interleaved(uint32_t saddr, uint32
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
 constexpr uint32_t kIdesc = idesc_bf16(128, 64);
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // fp16 A and B, fp32 D
 
 // four bytes -> two packed bf16x2 of their integer values, exact.
 // 0x4B000000 | v is the float 2^23 + v; subtracting 2^23 gives float(v) without the I2F pipe.
@@ -88,6 +94,18 @@ __device__ __forceinline__ uint2 bytes4_to_bf16x4(uint32_t x) {
   uint2 r;
   r.x = *reinterpret_cast<uint32_t*>(&a);
   r.y = *reinterpret_cast<uint32_t*>(&b);
+  return r;
+}
+
+// four bytes -> two packed fp16x2 of their integer values, exact: 0x6400 | v is the half 1024 + v.
+__device__ __forceinline__ uint2 bytes4_to_f16x4(uint32_t x) {
+  const uint32_t k1024 = 0x64006400u;
+  uint32_t a = __byte_perm(x, k1024, 0x7170), b = __byte_perm(x, k1024, 0x7372);
+  __half2 ha = __hsub2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<const __half2*>(&k1024));
+  __half2 hb = __hsub2(*reinterpret_cast<__half2*>(&b), *reinterpret_cast<const __half2*>(&k1024));
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&ha);
+  r.y = *reinterpret_cast<uint32_t*>(&hb);
   return r;
 }
 
@@ -116,7 +134,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 
 // kSplit: the output is SplitF words (bf16 hi | lo, FP32_TC precision) instead of bf16: the accumulators already carry
 // fp32 accuracy (exact bf16 pixels x bf16 hi + lo weights); only the pool buffers double (one CTA per SM then).
-template <bool kSplit>
+// kHalf (bf16 output only): pixels and weights in fp16, ONE pass over K = 64.  The weights of channel c are scaled by a
+// power of two into the top of the fp16 range (exact) and the sums scaled back in the epilogue's FFMA; an fp16 weight
+// is good to 2^-12 relative, eight times finer than the bf16 rounding of the output, so the second (lo) pass buys
+// nothing there -- and it was half of the kernel's MMA shared-memory traffic (48 KB per conv row).
+template <bool kSplit, bool kHalf>
 __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(const __grid_constant__ CUtensorMap map_x, const StemParams p) {
   constexpr int kPoolBuf = kSplit ? 2 * kPoolBytes : kPoolBytes;  // one pooled-row buffer: 128 columns x 64 channels
   constexpr int kPoolRow = kSplit ? 256 : 128;                    // bytes per column
@@ -128,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
   const uint32_t e_off = 0, b_off = kEBytes, pool_off = b_off + kBBytes, img_off = pool_off + 2 * kPoolBuf;
   const int img_bytes = kERows * p.pitch;
   const uint32_t bias_off = (img_off + img_bytes + 15u) & ~15u;
-  const uint32_t bar_off = bias_off + 64 * 4;
+  const uint32_t bar_off = bias_off + 128 * 4;  // bias[64], scale[64]
   auto e_ready = [&](int g) { return base + bar_off + 8u * g; };  // E rows [4g, 4g + 4) are built
   auto t_full = [&](int s) { return base + bar_off + 8u * (kEGroups + s); };
   auto t_empty = [&](int s) { return base + bar_off + 8u * (kEGroups + kSlots + s); };
@@ -160,7 +182,10 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
       p.trace[(blockIdx.x / 1000) * 64 + 6] = smid;
     }
   }
-  if (tid < 64) bias_sm[tid] = __ldg(p.bias + tid);
+  if (tid < 64) {
+    bias_sm[tid] = __ldg(p.bias + tid);
+    bias_sm[64 + tid] = __ldg(reinterpret_cast<const float*>(p.w_il) + kBBytes / 4 + tid);  // 1 / weight scale of the channel
+  }
   if (warp == 4) {
     if (lane == 0) {
       for (int g = 0; g < kEGroups; ++g) mbar_init(e_ready(g), 4);  // one arrival per builder warp
@@ -173,8 +198,9 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
       mbar_init_fence();
       // weight tile (16 KB, bulk copy) and, when the geometry allows, the u8 strip as ONE TMA box: pixel x of
       // input row y lands at img[(y - y_base) * pitch + x + kXOff]; out-of-image rows / columns are zero-filled
-      mbar_expect_tx(load_bar, (uint32_t)kBBytes + (p.use_tma ? (uint32_t)(kERows * p.pitch) : 0u));
-      bulk_load(base + b_off, p.w_il, kBBytes, load_bar);
+      constexpr uint32_t kWBytes = kHalf ? kBTile : kBBytes;
+      mbar_expect_tx(load_bar, kWBytes + (p.use_tma ? (uint32_t)(kERows * p.pitch) : 0u));
+      bulk_load(base + b_off, p.w_il, kWBytes, load_bar);
       // (the box must start on a 16-byte boundary of the row: x = -16, not -3)
       if (p.use_tma) tma_load_3d(base + img_off, &map_x, load_bar, -kXOff, y_base, image);
     }
@@ -213,7 +239,12 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
     const uint4 lo4 = src[0], hi4 = src[1];
     const uint32_t u0 = __funnelshift_r(lo4.w, hi4.x, 8), u1 = __funnelshift_r(hi4.x, hi4.y, 8);
     const uint32_t u2 = __funnelshift_r(hi4.y, hi4.z, 8), u3 = __funnelshift_r(hi4.z, hi4.w, 8);
-    const uint2 c0 = bytes4_to_bf16x4(u0), c1 = bytes4_to_bf16x4(u1), c2 = bytes4_to_bf16x4(u2), c3 = bytes4_to_bf16x4(u3);
+    uint2 c0, c1, c2, c3;
+    if constexpr (kHalf) {
+      c0 = bytes4_to_f16x4(u0), c1 = bytes4_to_f16x4(u1), c2 = bytes4_to_f16x4(u2), c3 = bytes4_to_f16x4(u3);
+    } else {
+      c0 = bytes4_to_bf16x4(u0), c1 = bytes4_to_bf16x4(u1), c2 = bytes4_to_bf16x4(u2), c3 = bytes4_to_bf16x4(u3);
+    }
     uint4* dst = reinterpret_cast<uint4*>(rowbuf + rr * p.rb_pitch + 32 * g);
     dst[0] = make_uint4(c0.x, c0.y, c1.x, c1.y);
     dst[1] = make_uint4(c2.x, c2.y, c3.x, c3.y);
@@ -256,12 +287,14 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
         const uint32_t a_s = base + e_off + (uint32_t)(2 * idx) * kERowBytes;  // E row of filter row 0
         const uint32_t d = tmem_base + (uint32_t)(slot * 64);
         // K = 128: the eight 16-byte K chunks (filter rows) against the hi weights, then again against the lo weights
+        // (kHalf: one pass, fp16 operands)
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass)
+        for (int pass = 0; pass < (kHalf ? 1 : 2); ++pass)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_w(d, smem_desc_interleaved(a_s + 2u * k * kERowBytes, kERowBytes, 128),
-                   smem_desc_interleaved(b_s + (uint32_t)pass * kBTile + 2u * k * 1024u, 1024, 128), kIdesc, (pass | k) != 0 ? 1u : 0u);
+                   smem_desc_interleaved(b_s + (uint32_t)pass * kBTile + 2u * k * 1024u, 1024, 128), kHalf ? kIdescF16 : kIdesc,
+                   (pass | k) != 0 ? 1u : 0u);
         tc_commit_w(t_full(slot));
       }
     }
@@ -350,7 +383,13 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
             for (int j = 0; j < 4; ++j) {
               const int e = qc * 16 + c * 8 + 2 * j;
               const float2 b2 = *reinterpret_cast<const float2*>(bias_sm + half * 32 + e);
-              __nv_bfloat162 t = __floats2bfloat162_rn(fmaxf(acc[e] + b2.x, 0.f), fmaxf(acc[e + 1] + b2.y, 0.f));
+              __nv_bfloat162 t;
+              if constexpr (kHalf) {
+                const float2 s2 = *reinterpret_cast<const float2*>(bias_sm + 64 + half * 32 + e);
+                t = __floats2bfloat162_rn(fmaxf(fmaf(acc[e], s2.x, b2.x), 0.f), fmaxf(fmaf(acc[e + 1], s2.y, b2.y), 0.f));
+              } else {
+                t = __floats2bfloat162_rn(fmaxf(acc[e] + b2.x, 0.f), fmaxf(acc[e + 1] + b2.y, 0.f));
+              }
               o[j] = *reinterpret_cast<uint32_t*>(&t);
             }
             *reinterpret_cast<uint4*>(pool + wo * 128 + (((4 * half + 2 * qc + c) ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -436,9 +475,37 @@ bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int poo
 // Two tiles (bf16 hi part, bf16 lo part of the weight) in the interleaved K-major layout: K chunk kc = filter
 // row r (8 of them, the last all zero), row n = output channel, element e = filter column s (e = 7 zero):
 // byte offset kc * 1024 + n * 16 + e * 2.
-int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out) {
-  std::vector<uint16_t> tile(kBBytes / 2, 0);
-  for (int o = 0; o < 64; ++o)
+// split = false (bf16 activations): ONE fp16 tile of w * 2^k(o), 2^k(o) the power of two that brings the channel's largest
+// weight into [2^13, 2^14); the 64 factors 2^-k(o) follow the tiles (floats at byte kBBytes).
+static bool stem_hilo_forced() {
+  static const bool f = getenv("SPK_STEM_HILO") != nullptr;  // A/B switch: the two-pass bf16 hi + lo kernel for bf16 output too
+  return f;
+}
+int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out, bool split) {
+  std::vector<uint16_t> tile(kBBytes / 2 + 128, 0);
+  float* inv_scale = reinterpret_cast<float*>(tile.data() + kBBytes / 2);
+  for (int o = 0; o < 64; ++o) inv_scale[o] = 1.f;
+  const bool half = !split && !stem_hilo_forced();
+  for (int o = 0; half && o < 64; ++o) {
+    double amax = 0.0;
+    for (int t = 0; t < 49; ++t) amax = std::max(amax, std::fabs((double)w[o * 49 + t] / 255.0));
+    int k = 0;
+    if (amax > 0.0 && std::isfinite(amax)) {
+      int e;
+      std::frexp(amax, &e);  // amax = m * 2^e, m in [0.5, 1)
+      k = 14 - e;            // amax * 2^k in [2^13, 2^14)
+      k = std::max(-60, std::min(60, k));
+    }
+    inv_scale[o] = (float)std::ldexp(1.0, -k);
+    for (int r = 0; r < 7; ++r)
+      for (int s = 0; s < 7; ++s) {
+        const __half hv = __float2half_rn((float)std::ldexp((double)w[(o * 7 + r) * 7 + s] / 255.0, k));
+        uint16_t b;
+        memcpy(&b, &hv, 2);
+        tile[(size_t)r * 512 + (size_t)o * 8 + s] = b;
+      }
+  }
+  for (int o = 0; !half && o < 64; ++o)
     for (int r = 0; r < 7; ++r)
       for (int s = 0; s < 7; ++s) {
         const float v = (float)((double)w[(o * 7 + r) * 7 + s] / 255.0);
@@ -450,8 +517,8 @@ int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out) {
         tile[(size_t)r * 512 + (size_t)o * 8 + s] = bh;
         tile[(size_t)kBTile / 2 + (size_t)r * 512 + (size_t)o * 8 + s] = bl;
       }
-  SPK_CUDA_OK(ctx, cudaMalloc(d_out, kBBytes));
-  SPK_CUDA_OK(ctx, cudaMemcpy(*d_out, tile.data(), kBBytes, cudaMemcpyHostToDevice));
+  SPK_CUDA_OK(ctx, cudaMalloc(d_out, kBBytes + 256));
+  SPK_CUDA_OK(ctx, cudaMemcpy(*d_out, tile.data(), kBBytes + 256, cudaMemcpyHostToDevice));
   return SPK_OK;
 }
 
@@ -493,12 +560,15 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     cache.th = th;
     cache.tw = tw;
   }
-  const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes * (split ? 2 : 1) + (size_t)kERows * p.pitch + 32 + 64 * 4 +
+  const size_t smem = 1024 + kEBytes + kBBytes + 2 * kPoolBytes * (split ? 2 : 1) + (size_t)kERows * p.pitch + 32 + 128 * 4 +
                       8 * (kEGroups + 3 + 2 * kSlots) + 16;
+  const bool half = !split && !stem_hilo_forced();  // (must agree with stem_pool_pack_weights)
   if (split)
-    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (half)
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else
-    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool want_trace = getenv("SPK_STEM_TRACE") != nullptr;
   static long long* d_trace = nullptr;
   static int trace_left = 3;
@@ -509,9 +579,11 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     p.trace = d_trace;
   }
   if (split)
-    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<true>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
+    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<true, false>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
+  else if (half)
+    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<false, true>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   else
-    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<false>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
+    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<false, false>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   SPK_LAUNCH_CHECK(ctx);
   if (p.trace) {
     --trace_left;

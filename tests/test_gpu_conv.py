@@ -174,7 +174,7 @@ def test_fused_stem_matches_unfused_and_torch(ctx, t, n):
     fused = run(_lib.CONV_AUTO)
     unfused = run(_lib.CONV_SIMT)
     # torch reference with the same folding: w' = sum_c w * gamma / sqrt(var + eps) / 255 (the kernel carries it as
-    # bf16 hi + bf16 lo, i.e. to 2^-17), integer pixels
+    # per-channel scaled fp16, i.e. to 2^-12; SPK_STEM_HILO=1 / fp32_tc: bf16 hi + bf16 lo, 2^-17), integer pixels
     scale = gamma.astype(np.float64) / np.sqrt(var.astype(np.float64) + BN_EPS)
     wf = (w.astype(np.float64).sum(axis=1) * scale[:, None, None])
     bias = (beta - mean * scale).astype(np.float32)
@@ -184,7 +184,12 @@ def test_fused_stem_matches_unfused_and_torch(ctx, t, n):
     ref = _bf16(ref.permute(0, 2, 3, 1).numpy())
     assert fused.shape == ref.shape == unfused.shape
     mag = max(1.0, float(np.abs(ref).max()))
-    assert float(np.abs(fused - ref).max()) <= 4e-3 * mag, float(np.abs(fused - ref).max())
+    # bf16 output of fp16 weights (2^-12 relative): element-wise within ONE bf16 step of the rounded reference
+    # (a value that sits next to a rounding boundary may land on the other side), and close on average
+    d = np.abs(fused - ref)
+    assert (d <= 2.0 ** -7 * np.abs(ref) + 1e-3 * mag).all(), float(d.max())
+    assert float(d.mean()) <= 2e-4 * mag, float(d.mean())
+    assert float((d > 0).mean()) <= 0.10, float((d > 0).mean())
     assert float(np.abs(fused - unfused).max()) <= 2e-2 * mag
 
 

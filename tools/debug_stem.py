@@ -48,7 +48,9 @@ def run(impl):
 for rep in range(3):
     fused = run(_lib.CONV_AUTO)
     ref = run(_lib.CONV_SIMT)
-    bad = np.abs(fused - ref) > 0.05
+    d = np.abs(fused - ref)
+    print("  differing elements %.4f%%, mean |d| %.3e, max |d| %.3e (ref mean |y| %.3f)" % (100.0 * (d > 0).mean(), d.mean(), d.max(), np.abs(ref).mean()))
+    bad = d > 0.05
     print("rep", rep, "bad elements", int(bad.sum()), "of", bad.size)
     if bad.any():
         im, r, c, ch = np.nonzero(bad)
