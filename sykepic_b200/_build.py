@@ -24,7 +24,7 @@ INCLUDE = ROOT / "include"
 BUILD = ROOT / "build" / "spk"
 LIB = PKG / "libsykepic_b200.so"
 
-SOURCES = ["host.cpp", "net.cu", "preprocess.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "conv_pair.cu", "conv_hp.cu", "stem.cu", "head.cu"]
+SOURCES = ["host.cpp", "net.cu", "preprocess.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "conv_pair.cu", "conv_hp.cu", "stem.cu", "stem_t.cu", "head.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", f"-I{INCLUDE}", f"-I{CSRC}"]

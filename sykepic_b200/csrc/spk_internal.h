@@ -178,6 +178,9 @@ void hp_conv_plan_set_reverse(HpConvPlan* p, int reverse);
 // stem.cu: conv 7x7/2 (1 gray plane -> 64) + bias + ReLU + maxpool 3x3/2 fused on tcgen05; u8 in -> bf16 NHWC out
 bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int pool_pad);
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w_folded /*[64][7][7]*/, uint4** d_out, bool split);
+int stem_pool_t_pack_weights(spk_ctx* ctx, const float* w_folded /*[64][7][7]*/, uint4** d_out);  // stem_t.cu
+int launch_stem_pool_t(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, const uint4* w, const float* bias, __nv_bfloat16* y,
+                       int hc, int wc, int hp, int wp, int ldy);
 int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, const uint4* w_sw, const float* bias,
                      __nv_bfloat16* y, int hc, int wc, int hp, int wp, int ldy, bool split = false);  // split: y holds SplitF words, ldy in words
 

@@ -477,11 +477,22 @@ bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int poo
 // byte offset kc * 1024 + n * 16 + e * 2.
 // split = false (bf16 activations): ONE fp16 tile of w * 2^k(o), 2^k(o) the power of two that brings the channel's largest
 // weight into [2^13, 2^14); the 64 factors 2^-k(o) follow the tiles (floats at byte kBBytes).
-static bool stem_hilo_forced() {
-  static const bool f = getenv("SPK_STEM_HILO") != nullptr;  // A/B switch: the two-pass bf16 hi + lo kernel for bf16 output too
-  return f;
+// Which kernel serves bf16 output -- A/B switch SPK_STEM: "t" (default) = the transposed kernel of stem_t.cu, "half" = this
+// file's kernel with fp16 operands in one pass, "hilo" = this file's kernel with bf16 hi + lo weights in two passes.
+// SplitF output (FP32_TC) always takes the hi + lo kernel.
+enum { kStemHilo = 0, kStemHalf = 1, kStemT = 2 };
+static int stem_variant(bool split) {
+  static const int v = [] {
+    const char* e = getenv("SPK_STEM");
+    if (e && !strcmp(e, "hilo")) return (int)kStemHilo;
+    if (e && !strcmp(e, "half")) return (int)kStemHalf;
+    return (int)kStemT;
+  }();
+  return split ? (int)kStemHilo : v;
 }
+static bool stem_hilo_forced() { return stem_variant(false) == kStemHilo; }
 int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out, bool split) {
+  if (stem_variant(split) == kStemT) return stem_pool_t_pack_weights(ctx, w, d_out);
   std::vector<uint16_t> tile(kBBytes / 2 + 128, 0);
   float* inv_scale = reinterpret_cast<float*>(tile.data() + kBBytes / 2);
   for (int o = 0; o < 64; ++o) inv_scale[o] = 1.f;
@@ -525,6 +536,7 @@ int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out, bool spl
 int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, const uint4* w_il, const float* bias,
                      __nv_bfloat16* y, int hc, int wc, int hp, int wp, int ldy, bool split) {
   if (n <= 0) return SPK_OK;
+  if (stem_variant(split) == kStemT) return launch_stem_pool_t(ctx, n, th, tw, x, w_il, bias, y, hc, wc, hp, wp, ldy);
   StemParams p;
   p.x = x;
   p.w_il = w_il;

@@ -174,7 +174,7 @@ def test_fused_stem_matches_unfused_and_torch(ctx, t, n):
     fused = run(_lib.CONV_AUTO)
     unfused = run(_lib.CONV_SIMT)
     # torch reference with the same folding: w' = sum_c w * gamma / sqrt(var + eps) / 255 (the kernel carries it as
-    # per-channel scaled fp16, i.e. to 2^-12; SPK_STEM_HILO=1 / fp32_tc: bf16 hi + bf16 lo, 2^-17), integer pixels
+    # per-channel scaled fp16, i.e. to 2^-12; SPK_STEM=hilo / fp32_tc: bf16 hi + bf16 lo, 2^-17), integer pixels
     scale = gamma.astype(np.float64) / np.sqrt(var.astype(np.float64) + BN_EPS)
     wf = (w.astype(np.float64).sum(axis=1) * scale[:, None, None])
     bias = (beta - mean * scale).astype(np.float32)

@@ -1,6 +1,6 @@
 """Probability error of a precision mode against the committed reference goldens, per test case
 (max and mean over all ROIs and classes).  Usage: python tools/bf16_error.py [precision=bf16]
-Used for A/B runs of kernel variants (e.g. SPK_STEM_HILO=1)."""
+Used for A/B runs of kernel variants (e.g. SPK_STEM=hilo)."""
 import sys
 import tempfile
 from pathlib import Path
