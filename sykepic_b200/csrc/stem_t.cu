@@ -19,7 +19,7 @@
 // the second conv row is the same filter two input rows further down.  Pixels and weights are fp16 (exact integers x
 // per-channel power-of-two scaled weights, 2^-12 relative; see stem.cu kHalf).
 //
-//   warps 0-3   build E rows from the converted strip (as stem.cu), then idle
+//   all warps   build the E rows from the converted strip (as stem.cu), two each; warps 0-3 then idle
 //   warp 4      TMEM allocation, 5 MMAs (K = 16 each) per accumulator, commits
 //   warps 5-12  epilogue: TMEM lane quarter q = warp % 4 is (conv row q / 2 of the pair, channels 32 (q % 2) + lane);
 //               the two warps of a quarter split the columns.  16 columns at a time: max over columns 2pw-1, 2pw,
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
         mbar_init(t_empty(s), kEpiWarps);
       }
       mbar_init(load_bar, 1);
-      mbar_init(built_bar, 4);  // one arrival per builder warp
+      mbar_init(built_bar, kThreads / 32);  // one arrival per warp
       mbar_init_fence();
       // weights (20 KB, bulk copy) and, when the geometry allows, the u8 strip as ONE TMA box: pixel x of input row y
       // lands at img[(y - y_base) * pitch + x + kXOff]; out-of-image rows / columns are zero-filled
@@ -202,10 +202,13 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
   }
   __syncthreads();
 
-  if (warp < 4) {
-    // ===== E builders: pure copies.  E[j] = bytes [4j, 4j + 16) of the row buffer; consecutive lanes take consecutive
-    // columns, so both the 4-byte loads and the 16-byte stores of a warp are contiguous =====
-    for (int yy = warp; yy < kERows; yy += 4) {
+  {
+    // ===== E rows: pure copies, by ALL 13 warps (two rows each) before they take up their roles: the MMA and epilogue warps
+    // have nothing to do until the first ten rows exist, and a single warp gets through a row in ~385 cycles (ncu: one
+    // instruction per 12.5 cycles and warp; four builder warps took 2500 cycles).  E[j] = bytes [4j, 4j + 16) of the row
+    // buffer; consecutive lanes take consecutive columns, so both the 4-byte loads and the 16-byte stores of a warp are
+    // contiguous =====
+    for (int yy = warp; yy < kERows; yy += kThreads / 32) {
       const unsigned char* r = rowbuf + yy * p.rb_pitch;
       unsigned char* e = gbase + e_off + yy * p.e_pitch;
 #pragma unroll
@@ -221,6 +224,9 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
       if (lane == 0) mbar_arrive(e_ready(yy >> 1));
     }
     if (lane == 0) mbar_arrive(built_bar);
+  }
+  if (warp < 4) {
+    // (idle from here on)
   } else if (warp == 4) {
     // ===== MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues =====
     const uint32_t w_s = base + w_off;
