@@ -53,7 +53,7 @@ constexpr int kERows = 26;                   // accumulator t reads E rows 4t ..
 constexpr int kEGroups = kERows / 2;         // the builders signal every 2 E rows
 constexpr int kWChunks = 10;
 constexpr int kWBytes = kWChunks * 128 * 16;  // weight operand: 10 K chunks x 128 rows x 8 fp16
-constexpr int kRing = 4;                      // conv rows (pooled width, bf16) kept for the vertical max
+constexpr int kRing = 6;                      // conv rows (pooled width, bf16) in flight between the epilogue and the store warps
 constexpr int kMaxT = 256;
 constexpr int kXOff = 16;  // column of pixel x = 0 in a strip row
 
@@ -66,7 +66,8 @@ struct StemTParams {
   int strips, pitch;
   int groups, rb_pitch;  // 16-pixel groups per strip row converted to fp16; byte pitch of the fp16 row buffer
   int ncols, e_pitch;    // N of the MMA (wc rounded up to 16); bytes per E row (16 per column)
-  int ring_pitch, region;  // bytes per ring row (128 per pooled column); bytes of the ring / row-buffer region
+  int ring_pitch, region;  // bytes per ring row (128 per pooled column); bytes of the ring / (row buffer + strip) region
+  int rb_bytes;            // bytes of the row buffer (rounded to 128): the strip follows it
   int use_tma;
 };
 
@@ -111,8 +112,15 @@ __device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ void sts_u16(unsigned char* p, uint32_t v) {
-  *reinterpret_cast<unsigned short*>(p) = (unsigned short)v;
+// shared-window addresses (32 bits) rather than generic pointers: with the generic forms the compiler rebuilt the window
+// base (S2UR SR_CgaCtaId + uniform-datapath arithmetic) in every 16-column piece
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr) : "memory");
+  return r;
 }
 
 __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_constant__ CUtensorMap map_x, const StemTParams p) {
@@ -120,16 +128,21 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 127u) & ~127u;
   unsigned char* gbase = smem_raw + (base - raw);
-  // layout: E | W | ring (aliases the fp16 row buffer) | image strip | barriers | tmem slot
-  const uint32_t e_off = 0, w_off = (uint32_t)(kERows * p.e_pitch), ring_off = w_off + kWBytes, img_off = ring_off + (uint32_t)p.region;
+  // layout: E | W | region: the ring, which aliases (fp16 row buffer | u8 image strip) | barriers | tmem slot
+  const uint32_t e_off = 0, w_off = (uint32_t)(kERows * p.e_pitch), ring_off = w_off + kWBytes, img_off = ring_off + (uint32_t)p.rb_bytes;
   const int img_bytes = kERows * p.pitch;
-  const uint32_t bar_off = (img_off + img_bytes + 15u) & ~15u;
+  const uint32_t bar_off = ring_off + (uint32_t)p.region;
   auto e_ready = [&](int g) { return base + bar_off + 8u * g; };  // E rows 2g, 2g + 1 are built
   auto t_full = [&](int s) { return base + bar_off + 8u * (kEGroups + s); };
   auto t_empty = [&](int s) { return base + bar_off + 8u * (kEGroups + kSlots + s); };
   const uint32_t load_bar = base + bar_off + 8u * (kEGroups + 2 * kSlots);
   const uint32_t built_bar = base + bar_off + 8u * (kEGroups + 2 * kSlots + 1);  // every E row is built: the ring may be written
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kEGroups + 2 * kSlots + 2));
+  // ring row slot s: written by the 4 epilogue warps of its conv row (ring_full), read by the 4 store warps (ring_empty)
+  auto ring_full = [&](int s) { return base + bar_off + 8u * (kEGroups + 2 * kSlots + 2 + s); };
+  auto ring_empty = [&](int s) { return base + bar_off + 8u * (kEGroups + 2 * kSlots + 2 + kRing + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * (kEGroups + 2 * kSlots + 2 + 2 * kRing));
+  const uint32_t ring_s = base + ring_off;
+  auto ring_slot = [](int idx) { return idx >= kRing ? idx - kRing : idx; };  // idx < 2 kRing
   unsigned char* ring = gbase + ring_off;
   unsigned char* rowbuf = ring;  // fp16 copy of the strip; idle once the E rows are built
   unsigned char* img = gbase + img_off;
@@ -156,6 +169,10 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
       }
       mbar_init(load_bar, 1);
       mbar_init(built_bar, kThreads / 32);  // one arrival per warp
+      for (int s = 0; s < kRing; ++s) {
+        mbar_init(ring_full(s), 4);
+        mbar_init(ring_empty(s), 4);
+      }
       mbar_init_fence();
       // weights (20 KB, bulk copy) and, when the geometry allows, the u8 strip as ONE TMA box: pixel x of input row y
       // lands at img[(y - y_base) * pitch + x + kXOff]; out-of-image rows / columns are zero-filled
@@ -226,7 +243,40 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
     if (lane == 0) mbar_arrive(built_bar);
   }
   if (warp < 4) {
-    // (idle from here on)
+    // ===== store warps (the builders' second job): per pooled row, wait for its three conv rows in the ring, take the
+    // vertical max (16-byte chunks of packed bf16), store coalesced, hand the ring rows that are no longer needed back.
+    // Runs beside the epilogue warps' next accumulator: with both jobs on the epilogue warps, separated by named barriers,
+    // an accumulator took 1100 + 1100 cycles =====
+    mbar_wait(built_bar, 0);  // (the ring aliases the row buffer; also orders this warp's own ring reads after every builder's reads)
+    int released = c_lo;      // conv rows below this one have been handed back
+    for (int prow = p0; prow <= p1; ++prow) {
+      const int r1 = 2 * prow;
+      const bool has0 = r1 - 1 >= 0, has2 = r1 + 1 <= p.hc - 1;
+      const int i1 = r1 - c_lo;
+      if (has0) mbar_wait(ring_full(ring_slot(i1 - 1)), (uint32_t)((i1 - 1) >= kRing));
+      mbar_wait(ring_full(ring_slot(i1)), (uint32_t)(i1 >= kRing));
+      if (has2) mbar_wait(ring_full(ring_slot(i1 + 1)), (uint32_t)((i1 + 1) >= kRing));
+      const uint32_t b1 = ring_s + (uint32_t)(ring_slot(i1) * p.ring_pitch);
+      const uint32_t b0 = has0 ? ring_s + (uint32_t)(ring_slot(i1 - 1) * p.ring_pitch) : b1;  // (a missing row reads the middle one again)
+      const uint32_t b2 = has2 ? ring_s + (uint32_t)(ring_slot(i1 + 1) * p.ring_pitch) : b1;
+      __nv_bfloat16* yrow = p.y + ((size_t)image * p.hp + prow) * p.wp * p.ldy;
+      for (int o = tid; o < p.wp * 8; o += 128) {
+        const int pw = o >> 3, j = o & 7;
+        const uint32_t off = (uint32_t)o * 16u;  // = pw * 128 + j * 16
+        uint4 m4 = lds_v4(b1 + off);
+        const uint4 t0 = lds_v4(b0 + off), t2 = lds_v4(b2 + off);
+        __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m4);
+        const __nv_bfloat162* q0 = reinterpret_cast<const __nv_bfloat162*>(&t0);
+        const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&t2);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mm[e] = __hmax2(__hmax2(mm[e], q0[e]), q2[e]);
+        *reinterpret_cast<uint4*>(yrow + (size_t)pw * p.ldy + j * 8) = m4;
+      }
+      // conv rows up to 2 prow are done with (2 prow + 1 also feeds the next pooled row)
+      __syncwarp();
+      for (; released <= r1; ++released)
+        if (lane == 0) mbar_arrive(ring_empty(ring_slot(released - c_lo)));
+    }
   } else if (warp == 4) {
     // ===== MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues =====
     const uint32_t w_s = base + w_off;
@@ -251,13 +301,11 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
     const int half = (warp - 5) >> 2;  // which part of the columns
     const int rowsel = q >> 1;         // conv row of the accumulator's pair
     const int ch = (q & 1) * 32 + lane;
-    const int et = tid - 160;  // 0..255 among the epilogue threads
     const float bias = __ldg(p.bias + ch);
     const float scale = __ldg(reinterpret_cast<const float*>(p.w) + kWBytes / 4 + ch);
     const int np = p.ncols >> 4;  // 16-column pieces
     const int kh = (np + 1) >> 1;
     const int k0 = half ? kh : 0, k1 = half ? np : kh;
-    int next_p = p0;
     for (int t = 0; t < n_acc; ++t) {
       const int slot = t & 1;
       const int idx = 2 * t + rowsel;
@@ -267,7 +315,9 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
       tc_fence_after();
       // the ring aliases the fp16 row buffer: wait until the builders have read all of it
       if (t == 0) mbar_wait(built_bar, 0);
-      unsigned char* hrow = ring + (idx & (kRing - 1)) * p.ring_pitch + ch * 2;
+      // the ring row's previous occupant (conv row idx - kRing) has been consumed by the store warps
+      if (row_ok && idx >= kRing) mbar_wait(ring_empty(ring_slot(idx)), 0);
+      const uint32_t hrow = ring_s + (uint32_t)(ring_slot(idx) * p.ring_pitch + ch * 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
       float carry = -INFINITY;  // conv column 16k - 1
       if (k0 > 0 && k0 < k1) {
@@ -284,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
           if (lane == 0) mbar_arrive(t_empty(slot));
         }
         if (row_ok) {
-          unsigned char* hp_ = hrow + (8 * k) * 128;
+          const uint32_t hp_ = hrow + (uint32_t)((8 * k) * 128);
           if (16 * k + 16 <= p.wc) {
 #pragma unroll
             for (int j = 0; j < 8; j += 2) {
@@ -315,37 +365,10 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty(slot));
       }
-      named_bar_sync(1, kEpiThreads);
-      // ---- pooled rows whose three conv rows are now in the ring: vertical max, coalesced 16-byte stores
-      const int done_row = c_lo + min(2 * t + 1, n_rows - 1);
-      while (next_p <= p1 && min(2 * next_p + 1, p.hc - 1) <= done_row) {
-        const int r1 = 2 * next_p;
-        const unsigned char* b1 = ring + ((r1 - c_lo) & (kRing - 1)) * p.ring_pitch;
-        const unsigned char* b0 = r1 - 1 >= 0 ? ring + ((r1 - 1 - c_lo) & (kRing - 1)) * p.ring_pitch : nullptr;
-        const unsigned char* b2 = r1 + 1 <= p.hc - 1 ? ring + ((r1 + 1 - c_lo) & (kRing - 1)) * p.ring_pitch : nullptr;
-        __nv_bfloat16* yrow = p.y + ((size_t)image * p.hp + next_p) * p.wp * p.ldy;
-        for (int o = et; o < p.wp * 8; o += kEpiThreads) {
-          const int pw = o >> 3, j = o & 7;
-          uint4 m4 = *reinterpret_cast<const uint4*>(b1 + pw * 128 + j * 16);
-          __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m4);
-          if (b0) {
-            const uint4 t4 = *reinterpret_cast<const uint4*>(b0 + pw * 128 + j * 16);
-            const __nv_bfloat162* tt = reinterpret_cast<const __nv_bfloat162*>(&t4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) mm[e] = __hmax2(mm[e], tt[e]);
-          }
-          if (b2) {
-            const uint4 t4 = *reinterpret_cast<const uint4*>(b2 + pw * 128 + j * 16);
-            const __nv_bfloat162* tt = reinterpret_cast<const __nv_bfloat162*>(&t4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) mm[e] = __hmax2(mm[e], tt[e]);
-          }
-          *reinterpret_cast<uint4*>(yrow + (size_t)pw * p.ldy + j * 8) = m4;
-        }
-        ++next_p;
+      if (row_ok) {  // this warp's part of conv row idx is in the ring
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ring_full(ring_slot(idx)));
       }
-      // the next accumulator's rows overwrite the two oldest ring rows, which the pass above may have read
-      if (t + 1 < n_acc) named_bar_sync(1, kEpiThreads);
     }
   }
 
@@ -416,7 +439,8 @@ int launch_stem_pool_t(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, co
   p.ncols = (wc + 15) / 16 * 16;
   p.e_pitch = p.ncols * 16;
   p.ring_pitch = wp * 128;
-  p.region = (std::max(kRing * p.ring_pitch, kERows * p.rb_pitch) + 127) / 128 * 128;
+  p.rb_bytes = (kERows * p.rb_pitch + 127) / 128 * 128;
+  p.region = (std::max(kRing * p.ring_pitch, p.rb_bytes + kERows * p.pitch) + 127) / 128 * 128;
   // the tensor map of the u8 batch {tw, th, n}, box {256, kERows, 1}: cached per (pointer, geometry)
   static thread_local struct { const void* x; int n, th, tw; CUtensorMap map; } cache = {nullptr, 0, 0, 0, {}};
   if (p.use_tma && (cache.x != x || cache.n < n || cache.th != th || cache.tw != tw)) {
@@ -433,8 +457,7 @@ int launch_stem_pool_t(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, co
     cache.th = th;
     cache.tw = tw;
   }
-  const size_t smem = 128 + (size_t)kERows * p.e_pitch + kWBytes + (size_t)p.region + (size_t)kERows * p.pitch + 16 +
-                      8 * (kEGroups + 2 * kSlots + 3) + 16;
+  const size_t smem = 128 + (size_t)kERows * p.e_pitch + kWBytes + (size_t)p.region + 8 * (kEGroups + 2 * kSlots + 3 + 2 * kRing) + 16;
   SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SPK_CUDA_OK(ctx, launch_pdl(stem_pool_t_kernel, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   SPK_LAUNCH_CHECK(ctx);
