@@ -320,51 +320,63 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
       const uint32_t hrow = ring_s + (uint32_t)(ring_slot(idx) * p.ring_pitch + ch * 2);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
       float carry = -INFINITY;  // conv column 16k - 1
-      if (k0 > 0 && k0 < k1) {
-        carry = tmem_ld1(taddr + (uint32_t)(16 * k0 - 1));
-        tmem_ld_wait();
-      }
-      for (int k = k0; k < k1; ++k) {
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)(16 * k), v);
-        tmem_ld_wait();
-        if (k == k1 - 1) {  // this warp has read its part of the accumulator
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty(slot));
-        }
-        if (row_ok) {
-          const uint32_t hp_ = hrow + (uint32_t)((8 * k) * 128);
-          if (16 * k + 16 <= p.wc) {
+      // 16 columns at a time, the next piece's tcgen05.ld in flight while this one is processed (a load + wait per piece
+      // left a ~100-cycle bubble in each)
+      auto piece = [&](const uint32_t (&v)[16], float cr, int k) {
+        const uint32_t hp_ = hrow + (uint32_t)((8 * k) * 128);
+        if (16 * k + 16 <= p.wc) {
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const float l0 = j == 0 ? carry : __uint_as_float(v[2 * j - 1]);
-              const float m0 = fmaxf(fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), l0);
-              const float m1 = fmaxf(fmaxf(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), __uint_as_float(v[2 * j + 1]));
-              const uint32_t o = relu_bf16x2(fmaf(m0, scale, bias), fmaf(m1, scale, bias));
-              sts_u16(hp_ + j * 128, o);
-              sts_u16(hp_ + (j + 1) * 128, o >> 16);
-            }
-          } else {  // the piece that holds the last conv column
+          for (int j = 0; j < 8; j += 2) {
+            const float l0 = j == 0 ? cr : __uint_as_float(v[2 * j - 1]);
+            const float m0 = fmaxf(fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), l0);
+            const float m1 = fmaxf(fmaxf(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), __uint_as_float(v[2 * j + 1]));
+            const uint32_t o = relu_bf16x2(fmaf(m0, scale, bias), fmaf(m1, scale, bias));
+            sts_u16(hp_ + j * 128, o);
+            sts_u16(hp_ + (j + 1) * 128, o >> 16);
+          }
+        } else {  // the piece that holds the last conv column
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int pw = 8 * k + j;
-              if (pw < p.wp) {
-                float m = __uint_as_float(v[2 * j]);
-                if (2 * pw + 1 < p.wc) m = fmaxf(m, __uint_as_float(v[2 * j + 1]));
-                m = fmaxf(m, j == 0 ? carry : __uint_as_float(v[2 * j - 1]));
-                sts_u16(hp_ + j * 128, relu_bf16x2(fmaf(m, scale, bias), 0.f));
-              }
+          for (int j = 0; j < 8; ++j) {
+            const int pw = 8 * k + j;
+            if (pw < p.wp) {
+              float m = __uint_as_float(v[2 * j]);
+              if (2 * pw + 1 < p.wc) m = fmaxf(m, __uint_as_float(v[2 * j + 1]));
+              m = fmaxf(m, j == 0 ? cr : __uint_as_float(v[2 * j - 1]));
+              sts_u16(hp_ + j * 128, relu_bf16x2(fmaf(m, scale, bias), 0.f));
             }
           }
         }
-        carry = __uint_as_float(v[15]);
-      }
-      if (k0 >= k1) {  // (a row of at most 16 conv columns: the second warp of the quarter only keeps the barrier counts)
+      };
+      auto release = [&]() {  // this warp has read its part of the accumulator
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(t_empty(slot));
+      };
+      uint32_t va[16], vb[16];
+      if (k0 < k1) {
+        if (k0 > 0) carry = tmem_ld1(taddr + (uint32_t)(16 * k0 - 1));
+        tmem_ld16(taddr + (uint32_t)(16 * k0), va);
       }
+      for (int k = k0; k < k1; k += 2) {
+        tmem_ld_wait();  // piece k (and, the first time, the carry)
+        const bool more1 = k + 1 < k1;
+        if (more1)
+          tmem_ld16(taddr + (uint32_t)(16 * (k + 1)), vb);
+        else
+          release();
+        if (row_ok) piece(va, carry, k);
+        carry = __uint_as_float(va[15]);
+        if (more1) {
+          tmem_ld_wait();  // piece k + 1
+          if (k + 2 < k1)
+            tmem_ld16(taddr + (uint32_t)(16 * (k + 2)), va);
+          else
+            release();
+          if (row_ok) piece(vb, carry, k + 1);
+          carry = __uint_as_float(vb[15]);
+        }
+      }
+      if (k0 >= k1) release();  // (a row of at most 16 conv columns: the second warp of the quarter only keeps the barrier counts)
       if (row_ok) {  // this warp's part of conv row idx is in the ring
         __syncwarp();
         if (lane == 0) mbar_arrive(ring_full(ring_slot(idx)));
