@@ -61,10 +61,46 @@ __global__ void __launch_bounds__(THREADS) head_kernel(const T* act, int hw, int
   // global average pool: sum over the hw positions in position order, then divide (fp32)
   const T* a = act + n * (long long)hw * F;
   const float inv = 1.0f / (float)hw;
-  for (int f = tid; f < F; f += THREADS) {
-    float s = 0.f;
-    for (int p = 0; p < hw; ++p) s += ld<T>(a + (long long)p * F + f);
-    feat[f] = s * inv;
+  if constexpr (sizeof(T) == 2) {
+    // bf16: two adjacent features per thread and load (same per-feature summation order), eight positions in flight
+    if ((F & 1) == 0) {
+      for (int f = 2 * tid; f < F; f += 2 * THREADS) {
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(a + f);
+        const int ld2 = F >> 1;
+        float s0 = 0.f, s1 = 0.f;
+        int p = 0;
+        for (; p + 8 <= hw; p += 8) {
+          __nv_bfloat162 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = a2[(long long)(p + u) * ld2];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float2 t = __bfloat1622float2(v[u]);
+            s0 += t.x;
+            s1 += t.y;
+          }
+        }
+        for (; p < hw; ++p) {
+          const float2 t = __bfloat1622float2(a2[(long long)p * ld2]);
+          s0 += t.x;
+          s1 += t.y;
+        }
+        feat[f] = s0 * inv;
+        feat[f + 1] = s1 * inv;
+      }
+    } else {
+      for (int f = tid; f < F; f += THREADS) {
+        float s = 0.f;
+        for (int p = 0; p < hw; ++p) s += ld<T>(a + (long long)p * F + f);
+        feat[f] = s * inv;
+      }
+    }
+  } else {
+    for (int f = tid; f < F; f += THREADS) {
+      float s = 0.f;
+      for (int p = 0; p < hw; ++p) s += ld<T>(a + (long long)p * F + f);
+      feat[f] = s * inv;
+    }
   }
   __syncthreads();
 
