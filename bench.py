@@ -318,8 +318,10 @@ def run_b200(args):
     h0, h1 = submit_host(0), submit_host(1)
     h0.result()
     h1.result()
+    for i in range(2):  # ... and two more at steady state (host threads and clocks up on every rank)
+        submit_host(i).result()
     barrier()
-    e2e_calls = max(8, -(-args.steps // G))
+    e2e_calls = max(24, -(-args.steps // G))  # >= 0.4 s per rank: eight calls were at the mercy of one slow host thread
     t0 = time.perf_counter()
     # the host API as `probability.main` drives it (pipeline.BinPipeline): bin i+1 is submitted before bin i is awaited
     pending = None
