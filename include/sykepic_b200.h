@@ -197,6 +197,17 @@ int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64
  * strict = 1: smallest q with value > thr                                    (scalar threshold, prediction.py:58-59) */
 int32_t spk_threshold_quantize(double thr, int strict);
 
+/* ---- image mode: PNG scanline filters (host) ----------------------------------------------
+ * `sykepic prob --image-dir / --images` (compute/probability.py:28-36,165-177) reads ROI
+ * images with cv2.imread (train/data.py:217-219).  Here the PNG container and zlib stream are
+ * handled by the Python host; this reverses the five scanline filters (None, Sub, Up, Average,
+ * Paeth) of the inflated IDAT data, the only per-byte sequential part of the decode.
+ *   raw     h rows of (1 filter-type byte + stride bytes)
+ *   bpp     bytes per pixel (1 gray, 2 gray+alpha, 3 RGB, 4 RGBA; 8-bit samples)
+ *   out     h * stride bytes, the unfiltered samples
+ * SPK_ERR_PARSE on an unknown filter type. */
+int spk_png_unfilter(const uint8_t* raw, int64_t h, int64_t stride, int bpp, uint8_t* out);
+
 /* ---- A9: .prob.csv formatting (host) ----------------------------------------------------
  * Replaces probabilities_to_csv (compute/probability.py:200-206): header line, then per
  * ROI "<id>,<p:.5f>,...\n" with p widened to double and correctly rounded.

@@ -22,6 +22,7 @@ and one host thread per GPU, no collective -- SURVEY.md 8e).
 import os
 import threading
 from collections import namedtuple
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
@@ -302,11 +303,11 @@ def process_images(img_paths, net, params, csv_path, force=False):
             return
     from .. import png
 
-    rois, ids = [], []
-    for p in img_paths:
-        img = png.read_gray(p)
-        rois.append(img)
-        ids.append(int(Path(p).stem.split("_")[-1]))
+    # file read, zlib inflate and the scanline filters (C ABI) all run without the GIL: decode on a few threads, in order
+    img_paths = list(img_paths)
+    ids = [int(Path(p).stem.split("_")[-1]) for p in img_paths]
+    with ThreadPoolExecutor(max(1, min(8, os.cpu_count() or 1))) as pool:
+        rois = list(pool.map(png.read_gray, img_paths))
     probabilities = net_pass(net, list(zip(ids, rois)), batch_size=params.batch_size)
     probabilities_to_csv(probabilities, params.classes, csv_path)
 

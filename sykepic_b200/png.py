@@ -2,8 +2,8 @@
 
 The reference reads ROI images with `cv2.imread` (train/data.py:217-219); IFCB ROI
 PNGs are 8-bit grayscale, so the three planes it feeds the network are identical.
-Here the file is decoded to ONE gray plane (zlib + the five PNG filters, numpy) and
-takes the same device path as a raw bin.  8-bit gray / gray+alpha / RGB(A) with equal
+Here the file is decoded to ONE gray plane (zlib inflate, then the five PNG filters in the C-ABI
+host library) and takes the same device path as a raw bin.  8-bit gray / gray+alpha / RGB(A) with equal
 channels, non-interlaced.
 """
 
@@ -11,6 +11,8 @@ import struct
 import zlib
 
 import numpy as np
+
+from . import _lib
 
 
 def read_gray(path):
@@ -37,37 +39,13 @@ def read_gray(path):
         raise ValueError(f"{path}: unsupported PNG (depth {depth}, colour type {ctype}, interlace {interlace})")
     raw = np.frombuffer(zlib.decompress(b"".join(idat)), np.uint8)
     stride = w * chans
-    raw = raw.reshape(h, stride + 1)
-    out = np.zeros((h, stride), np.uint8)
-    prev = np.zeros(stride, np.int32)
-    for y in range(h):
-        f = int(raw[y, 0])
-        line = raw[y, 1:].astype(np.int32)
-        if f == 0:
-            cur = line
-        elif f == 2:
-            cur = (line + prev) & 255
-        elif f == 1 and chans == 1:
-            cur = np.cumsum(line) & 255
-        else:  # Sub (multi-channel), Average, Paeth: sequential in x
-            cur = np.zeros(stride, np.int32)
-            for x in range(stride):
-                a = cur[x - chans] if x >= chans else 0
-                b = prev[x]
-                c = prev[x - chans] if x >= chans else 0
-                if f == 1:
-                    pred = a
-                elif f == 3:
-                    pred = (a + b) >> 1
-                elif f == 4:
-                    p = a + b - c
-                    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
-                    pred = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
-                else:
-                    raise ValueError(f"{path}: bad filter {f}")
-                cur[x] = (line[x] + pred) & 255
-        out[y] = cur
-        prev = cur
+    if raw.size != h * (stride + 1):
+        raise ValueError(f"{path}: {raw.size} bytes of image data, expected {h * (stride + 1)}")
+    # the five scanline filters: sequential per byte, done by the C-ABI host library (spk_png_unfilter)
+    out = np.empty((h, stride), np.uint8)
+    rc = _lib.load().spk_png_unfilter(raw.ctypes.data, h, stride, chans, out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"{path}: {_lib.last_error()}")
     img = out.reshape(h, w, chans)
     if chans >= 3 and not (np.array_equal(img[..., 0], img[..., 1]) and np.array_equal(img[..., 0], img[..., 2])):
         raise ValueError(f"{path}: colour PNG; IFCB ROI images are grayscale")

@@ -1,0 +1,142 @@
+"""PNG decode of the image mode (`sykepic prob --image-dir/--images`): sykepic_b200/png.py + spk_png_unfilter (C ABI, host)
+against cv2.imread, which is what the reference uses (sykepic/train/data.py:217-219), and against hand-filtered files
+that force each of the five scanline filters."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from sykepic_b200 import _lib, png, synth
+
+
+def _chunk(typ, body):
+    return struct.pack(">I", len(body)) + typ + body + struct.pack(">I", zlib.crc32(typ + body) & 0xFFFFFFFF)
+
+
+def _paeth(a, b, c):
+    p = a + b - c
+    pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+    return a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+
+
+def write_png(path, img, filters, ctype=0):
+    """Encode `img` ([h, w] or [h, w, chans] uint8) with the given filter type per row (cycled)."""
+    img = np.asarray(img, np.uint8)
+    h, w = img.shape[:2]
+    chans = 1 if img.ndim == 2 else img.shape[2]
+    rows = img.reshape(h, w * chans).astype(np.int32)
+    stride = w * chans
+    raw = bytearray()
+    for y in range(h):
+        f = filters[y % len(filters)]
+        cur, prev = rows[y], rows[y - 1] if y else np.zeros(stride, np.int32)
+        line = np.empty(stride, np.int32)
+        for x in range(stride):
+            a = cur[x - chans] if x >= chans else 0
+            b = prev[x]
+            c = prev[x - chans] if x >= chans else 0
+            pred = [0, a, b, (a + b) >> 1, _paeth(a, b, c)][f]
+            line[x] = (cur[x] - pred) & 255
+        raw.append(f)
+        raw += line.astype(np.uint8).tobytes()
+    data = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0))
+    comp = zlib.compress(bytes(raw), 6)
+    half = len(comp) // 2  # two IDAT chunks: the stream may be split anywhere
+    data += _chunk(b"IDAT", comp[:half]) + _chunk(b"IDAT", comp[half:]) + _chunk(b"IEND", b"")
+    path.write_bytes(data)
+
+
+@pytest.mark.parametrize("filters", [[0], [1], [2], [3], [4], [4, 3, 2, 1, 0], [1, 4]], ids=str)
+def test_every_filter_type(tmp_path, filters):
+    rng = np.random.default_rng(sum(filters) + len(filters))
+    for w, h in [(1, 1), (2, 3), (17, 9), (88, 50)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        write_png(tmp_path / "g.png", img, filters)
+        assert np.array_equal(png.read_gray(tmp_path / "g.png"), img)
+        # gray replicated into RGB / RGBA / gray+alpha (what some tools write for the same picture)
+        for ctype, chans in ((2, 3), (6, 4), (4, 2)):
+            multi = np.repeat(img[..., None], chans, axis=2)
+            if chans in (2, 4):
+                multi[..., -1] = 255
+            write_png(tmp_path / "m.png", multi, filters, ctype)
+            assert np.array_equal(png.read_gray(tmp_path / "m.png"), img)
+
+
+def test_matches_cv2_on_roi_images(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for k in range(40):
+        w, h = int(rng.integers(8, 400)), int(rng.integers(4, 200))
+        img = synth.synth_roi_pixels(rng, w, h) if k % 2 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+        path = tmp_path / f"D20210523T000000_IFCB114_{k:05d}.png"
+        assert cv2.imwrite(str(path), img)  # the reference writes ROI images with cv2 (utils/ifcb.py:118)
+        ref = cv2.imread(str(path))  # colour read of a gray file: three identical planes (train/data.py:217-219)
+        got = png.read_gray(path)
+        assert np.array_equal(got, img) and np.array_equal(ref[..., 0], got) and np.array_equal(ref[..., 2], got)
+
+
+def test_rejects_what_the_path_cannot_take(tmp_path):
+    rng = np.random.default_rng(1)
+    colour = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    write_png(tmp_path / "c.png", colour, [0], ctype=2)
+    with pytest.raises(ValueError, match="colour"):
+        png.read_gray(tmp_path / "c.png")
+    (tmp_path / "n.png").write_bytes(b"not a png at all")
+    with pytest.raises(ValueError, match="not a PNG"):
+        png.read_gray(tmp_path / "n.png")
+    # an unknown filter type comes back from the C ABI as SPK_ERR_PARSE
+    raw = np.array([7, 1, 2, 3], np.uint8)
+    out = np.empty(3, np.uint8)
+    assert _lib.load().spk_png_unfilter(raw.ctypes.data, 1, 3, 1, out.ctypes.data) == _lib.SPK_ERR_PARSE
+    # truncated image data
+    w, h = 7, 5
+    stream = b"".join(b"\x00" + bytes(range(w)) for _ in range(h))[:-3]
+    data = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0))
+    (tmp_path / "s.png").write_bytes(data + _chunk(b"IDAT", zlib.compress(stream)) + _chunk(b"IEND", b""))
+    with pytest.raises(ValueError, match="bytes of image data"):
+        png.read_gray(tmp_path / "s.png")
+
+
+def test_process_images_decodes_in_order(tmp_path):
+    """`process_images` (probability.py:165-177 of the reference) with a stand-in engine: the PNGs of one sample are
+    decoded on the thread pool, packed in the order given and the CSV comes out sorted by ROI id (:197)."""
+    from collections import namedtuple
+
+    from sykepic_b200.compute import probability
+
+    rng = np.random.default_rng(3)
+    sample = "D20210523T000000_IFCB114"
+    ids = [7, 2, 11, 3, 5, 40, 1]
+    imgs = {}
+    for k, i in enumerate(ids):
+        img = rng.integers(0, 256, (4 + k, 9 + 2 * k), dtype=np.uint8)
+        imgs[i] = img
+        write_png(tmp_path / f"{sample}_{i:05d}.png", img, [4, 1, 3])
+
+    class Net:
+        def run_rois(self, roi_id, w, h, start, data, batch_size=None):
+            # "probabilities" that identify the picture behind each descriptor
+            out = np.zeros((len(w), 2), np.float32)
+            for k in range(len(w)):
+                px = data[int(start[k]): int(start[k]) + int(w[k]) * int(h[k])].reshape(int(h[k]), int(w[k]))
+                assert np.array_equal(px, imgs[int(roi_id[k])])
+                out[k] = (float(px[0, 0]) / 255.0, float(px[-1, -1]) / 255.0)
+            return out
+
+    params = namedtuple("P", "classes batch_size")(["a", "b"], 4)
+    csv_path = tmp_path / "out" / f"{sample}.prob.csv"
+    probability.process_images([tmp_path / f"{sample}_{i:05d}.png" for i in ids], Net(), params, csv_path)
+    lines = csv_path.read_text().splitlines()
+    assert lines[0] == "roi,a,b" and [int(l.split(",")[0]) for l in lines[1:]] == sorted(ids)
+    for l in lines[1:]:
+        i, a, b = l.split(",")
+        img = imgs[int(i)]
+        assert a == f"{np.float32(img[0, 0] / np.float32(255.0)):.5f}" or abs(float(a) - img[0, 0] / 255.0) < 1e-5
+        assert abs(float(b) - img[-1, -1] / 255.0) < 1e-5
+    # existing file: skipped unless forced (probability.py:136-141)
+    csv_path.write_text("sentinel")
+    probability.process_images([tmp_path / f"{sample}_{ids[0]:05d}.png"], Net(), params, csv_path)
+    assert csv_path.read_text() == "sentinel"
+    probability.process_images([tmp_path / f"{sample}_{ids[0]:05d}.png"], Net(), params, csv_path, force=True)
+    assert csv_path.read_text().startswith("roi,a,b\n7,")
