@@ -123,10 +123,13 @@ def main(
 
     if samples_as_images:
         net, params = make_params(devices[0])
-        items = list(sample_paths.items())
-        for sample, img_paths in _progress(items, progress_bar):
-            csv_path = Path(out_dir) / f"{sample}{FILE_SUFFIX}.csv"
-            process_images(img_paths, net, params, csv_path, force)
+        try:
+            items = list(sample_paths.items())
+            for sample, img_paths in _progress(items, progress_bar):
+                csv_path = Path(out_dir) / f"{sample}{FILE_SUFFIX}.csv"
+                process_images(img_paths, net, params, csv_path, force)
+        finally:
+            net.close()
         return None
 
     sample_paths = list(sample_paths)

@@ -181,6 +181,40 @@ def test_cli_prob_then_class(model_dirs, tmp_path):
     assert lines[0].startswith("Time,") and len(lines) == 4
 
 
+def test_image_mode_matches_raw_mode(engines, model_dirs, tmp_path):
+    """SURVEY 8f rank 1, `sykepic prob --image-dir`: the ROIs of two bins written as `<sample>_<roi>.png` (what
+    ifcb.raw_to_png produces, sykepic/utils/ifcb.py:76-118) go through `probability.call` and give the raw mode's
+    probabilities (same kernels, same bytes), one CSV per sample directly under OUT (probability.py:96)."""
+    from types import SimpleNamespace
+
+    from tests.test_host_png import write_png_up
+
+    case = "r18_180"
+    eng = engines(case, "fp32")
+    img_dir = tmp_path / "imgs"
+    img_dir.mkdir()
+    expected = {}
+    for bname, b in case_bins(case)[:2]:  # the reference's fixture bin and the edge-geometry bin
+        rid, w, h, start = engine.parse_adc(b["adc_text"])
+        for i, ww, hh, s in zip(rid, w, h, start):
+            px = np.asarray(b["roi_bytes"][int(s): int(s) + int(ww) * int(hh)]).reshape(int(hh), int(ww))
+            write_png_up(img_dir / f"{bname}_{int(i):05d}.png", px)
+        rid2, probs = eng.run_bin(b["adc_text"], b["roi_bytes"])
+        assert np.array_equal(rid2, rid)
+        expected[bname] = (rid2, probs)
+    out = tmp_path / "out"
+    args = SimpleNamespace(image_dir=str(img_dir), images=None, raw=None, samples=None, model=str(model_dirs(case)), out=str(out),
+                           batch_size=64, num_workers=2, force=False, precision="fp32", devices=None)
+    assert probability.call(args) is None  # the reference returns nothing in image mode (probability.py:94-97)
+    assert sorted(p.name for p in out.iterdir()) == sorted(f"{b}.prob.csv" for b in expected)
+    for bname, (rid, probs) in expected.items():
+        lines = (out / f"{bname}.prob.csv").read_text().splitlines()
+        assert lines[0] == "roi," + ",".join(eng.spec.classes)
+        got = np.array([[float(x) for x in l.split(",")[1:]] for l in lines[1:]], np.float64)
+        assert [int(l.split(",")[0]) for l in lines[1:]] == rid.tolist()
+        assert np.abs(got - probs).max() <= 1e-5 + 5e-6  # 5 decimals of the same fp32 values (launch size differs: 1024 vs 64)
+
+
 def test_densenet121_matches_oracle(tmp_path):
     """BASELINE config 4.  The reference raises for DenseNet at these sizes, so there is no golden
     from it: the defined behaviour (torchvision's forward + the syke-pic head) is checked against the oracle's
