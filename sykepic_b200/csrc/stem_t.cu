@@ -7,11 +7,12 @@
 //   stem.cu    D[conv column (TMEM lane)][channel (TMEM column)]   = E (pixels) x W^T
 //   here       D[channel, conv row parity (lane)][conv column (TMEM column)] = W2 x E^T
 //
-// stem.cu is bound by instruction issue (31 k warp-instructions per strip of 4 pooled rows): with conv columns on the
-// lanes, the horizontal half of the 3x3 max needs a trip through shared memory at full conv resolution, and bias /
-// ReLU / rounding run on 2 x 64 lanes' worth of elements per pooled one.  With the conv columns of one channel in ONE
-// thread's registers the horizontal max is two FMNMX per pooled element, bias and scale are per-thread scalars, and
-// only pooled-width bf16 rows go through shared memory for the vertical max and the NHWC transpose.
+// stem.cu reads every conv row's accumulator 1.5 times out of TMEM and spends 31 k warp-instructions per strip of 4 pooled
+// rows: with conv columns on the lanes, the horizontal half of the 3x3 max needs a trip through shared memory at full conv
+// resolution, and bias / ReLU / rounding run on 2 x 64 lanes' worth of elements per pooled one.  With the conv columns of
+// one channel in ONE thread's registers the horizontal max is one FMNMX3 per pooled element, bias and scale are per-thread
+// scalars, and only pooled-width bf16 rows go through shared memory for the vertical max and the NHWC transpose
+// (17 k warp-instructions per strip).
 //
 // GEMM per accumulator (two conv rows i, i + 1): M = 128 = 64 channels x 2 conv rows, N = the row's conv columns
 // rounded up to 16 (112 at T = 224), K = 10 x 8: K chunk q is INPUT row 2i - 3 + q (E row, 8 taps wide, as in
@@ -19,13 +20,16 @@
 // the second conv row is the same filter two input rows further down.  Pixels and weights are fp16 (exact integers x
 // per-channel power-of-two scaled weights, 2^-12 relative; see stem.cu kHalf).
 //
-//   all warps   build the E rows from the converted strip (as stem.cu), two each; warps 0-3 then idle
+//   all warps   convert the strip to fp16 once, then build the E rows (two each)
+//   warps 0-3   then: STORE warps -- per pooled row, wait for its three conv rows in the ring (mbarriers per ring row),
+//               maximum of the three (16-byte chunks, packed bf16 max), coalesced stores, ring rows handed back
 //   warp 4      TMEM allocation, 5 MMAs (K = 16 each) per accumulator, commits
 //   warps 5-12  epilogue: TMEM lane quarter q = warp % 4 is (conv row q / 2 of the pair, channels 32 (q % 2) + lane);
-//               the two warps of a quarter split the columns.  16 columns at a time: max over columns 2pw-1, 2pw,
-//               2pw+1, x scale + bias, ReLU + bf16 (cvt.rn.relu.bf16x2), 2-byte stores into the conv row's slot of a
-//               4-row ring [pooled column][channel]; then, per finished pooled row, all 256 threads take the
-//               maximum of its three ring rows (16-byte chunks, packed bf16 max) and store it, coalesced.
+//               the two warps of a quarter split the columns.  16 columns at a time (the next tcgen05.ld in flight):
+//               max over columns 2pw-1, 2pw, 2pw+1, x scale + bias, ReLU + bf16 (cvt.rn.relu.bf16x2), 2-byte stores
+//               into the conv row's slot of a 6-row ring [pooled column][channel]
+// Measured (finding 6): 0.127 ms per 256 images against 0.161 ms for stem.cu; latency- and
+// occupancy-bound (two CTAs per SM, one instruction per ~12 cycles and warp), the step around it power-capped.
 // Replaces conv1 / bn1 / relu / maxpool of torchvision's ResNet as run by TorchVisionNet.forward
 // (sykepic/train/network.py:66-68).
 #include <cuda.h>
@@ -46,7 +50,7 @@ using namespace tc;
 
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 160 + kEpiThreads;  // 4 builder warps + 1 MMA warp + 8 epilogue warps
+constexpr int kThreads = 160 + kEpiThreads;  // 4 store warps + 1 MMA warp + 8 epilogue warps
 constexpr int kSlots = 2;                    // TMEM accumulator ring: 2 x 128 columns (two CTAs share the SM's 512)
 constexpr int kPoolRowsPerStrip = 4;
 constexpr int kERows = 26;                   // accumulator t reads E rows 4t .. 4t + 9, t <= 4
@@ -54,7 +58,6 @@ constexpr int kEGroups = kERows / 2;         // the builders signal every 2 E ro
 constexpr int kWChunks = 10;
 constexpr int kWBytes = kWChunks * 128 * 16;  // weight operand: 10 K chunks x 128 rows x 8 fp16
 constexpr int kRing = 6;                      // conv rows (pooled width, bf16) in flight between the epilogue and the store warps
-constexpr int kMaxT = 256;
 constexpr int kXOff = 16;  // column of pixel x = 0 in a strip row
 
 struct StemTParams {
