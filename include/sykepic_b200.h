@@ -208,6 +208,17 @@ int32_t spk_threshold_quantize(double thr, int strict);
  * SPK_ERR_PARSE on an unknown filter type. */
 int spk_png_unfilter(const uint8_t* raw, int64_t h, int64_t stride, int bpp, uint8_t* out);
 
+/* A whole sample's ROI images at once, on `threads` host threads (0 = all cores, at most 16), straight into one byte
+ * stream laid out like a `.roi` file -- what the DataLoader workers' cv2.imread calls produce one by one in the reference
+ * (train/data.py:217-219).  8-bit gray / gray+alpha / RGB(A) with equal colour channels, non-interlaced; chunk CRCs are
+ * checked (libpng rejects such files too).
+ *   spk_png_probe          width / height of every file (reads the 33-byte IHDR prefix only)
+ *   spk_png_decode_batch   file i -> out[start[i] .. start[i] + width[i] * height[i]) as one gray plane
+ * SPK_ERR_PARSE with the path and reason in spk_last_error(NULL), *first_bad = index of the first offending file. */
+int spk_png_probe(const char* const* paths, int64_t n, int32_t* width, int32_t* height, int threads, int64_t* first_bad);
+int spk_png_decode_batch(const char* const* paths, int64_t n, const int32_t* width, const int32_t* height, const int64_t* start,
+                         uint8_t* out, int64_t out_len, int threads, int64_t* first_bad);
+
 /* ---- A9: .prob.csv formatting (host) ----------------------------------------------------
  * Replaces probabilities_to_csv (compute/probability.py:200-206): header line, then per
  * ROI "<id>,<p:.5f>,...\n" with p widened to double and correctly rounded.

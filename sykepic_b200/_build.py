@@ -24,7 +24,7 @@ INCLUDE = ROOT / "include"
 BUILD = ROOT / "build" / "spk"
 LIB = PKG / "libsykepic_b200.so"
 
-SOURCES = ["host.cpp", "net.cu", "preprocess.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "conv_pair.cu", "conv_hp.cu", "stem.cu", "stem_t.cu", "head.cu"]
+SOURCES = ["host.cpp", "png.cpp", "net.cu", "preprocess.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "conv_pair.cu", "conv_hp.cu", "stem.cu", "stem_t.cu", "head.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", f"-I{INCLUDE}", f"-I{CSRC}"]
@@ -78,7 +78,7 @@ def build(force=False, verbose=False):
         for _, _, stamp, want in jobs:
             stamp.write_text(want)
     if jobs or not LIB.exists():
-        cmd = [nvcc(), *ARCH, "-shared", "-cudart", "static", "-o", str(LIB), *map(str, objs)]
+        cmd = [nvcc(), *ARCH, "-shared", "-cudart", "static", "-o", str(LIB), *map(str, objs), "-lz"]  # zlib: png.cpp
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

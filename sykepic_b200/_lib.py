@@ -86,6 +86,8 @@ PROTOTYPES = {
     "spk_threshold_quantize": (C.c_int32, [C.c_double, _i]),
     "spk_format_prob_csv": (_i, [C.c_char_p, _p, _p, _i64, _i, _p, _i64, C.POINTER(_i64)]),
     "spk_png_unfilter": (_i, [_p, _i64, _i64, _i, _p]),
+    "spk_png_probe": (_i, [_p, _i64, _p, _p, _i, C.POINTER(_i64)]),
+    "spk_png_decode_batch": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, C.POINTER(_i64)]),
 }
 
 _lib = None

@@ -22,7 +22,6 @@ and one host thread per GPU, no collective -- SURVEY.md 8e).
 import os
 import threading
 from collections import namedtuple
-from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
@@ -306,13 +305,15 @@ def process_images(img_paths, net, params, csv_path, force=False):
             return
     from .. import png
 
-    # file read, zlib inflate and the scanline filters (C ABI) all run without the GIL: decode on a few threads, in order
+    # all files of the sample -> one byte stream (the layout of a `.roi` file), decoded by the host library's threads
     img_paths = list(img_paths)
-    ids = [int(Path(p).stem.split("_")[-1]) for p in img_paths]
-    with ThreadPoolExecutor(max(1, min(8, os.cpu_count() or 1))) as pool:
-        rois = list(pool.map(png.read_gray, img_paths))
-    probabilities = net_pass(net, list(zip(ids, rois)), batch_size=params.batch_size)
-    probabilities_to_csv(probabilities, params.classes, csv_path)
+    ids = np.array([int(Path(p).stem.split("_")[-1]) for p in img_paths], np.int32)
+    w, h, start, data = png.read_gray_many(img_paths)
+    if len(ids):
+        probs = net.run_rois(ids, w, h, start, data, batch_size=params.batch_size)
+        _write_csv(ids, probs, params.classes, csv_path)  # sorted by ROI id there (probability.py:197)
+    else:
+        probabilities_to_csv([], params.classes, csv_path)
 
 
 def net_pass(net, rois, device=None, batch_size=None):

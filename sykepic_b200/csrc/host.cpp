@@ -294,49 +294,4 @@ int spk_format_prob_csv(const char* header_line, const int32_t* roi_id, const fl
   return SPK_OK;
 }
 
-int spk_png_unfilter(const uint8_t* raw, int64_t h, int64_t stride, int bpp, uint8_t* out) {
-  if (!raw || !out || h < 0 || stride < 0 || bpp < 1 || bpp > 4) return fail(nullptr, SPK_ERR_INVALID, "spk_png_unfilter: bad argument");
-  const uint8_t* prev = nullptr;
-  for (int64_t y = 0; y < h; ++y) {
-    const uint8_t* line = raw + y * (stride + 1);
-    const int f = line[0];
-    ++line;
-    uint8_t* cur = out + y * stride;
-    const int64_t head = stride < bpp ? stride : bpp;  // the first pixel has no left neighbour
-    switch (f) {
-      case 0:
-        memcpy(cur, line, (size_t)stride);
-        break;
-      case 1:  // Sub
-        for (int64_t x = 0; x < head; ++x) cur[x] = line[x];
-        for (int64_t x = head; x < stride; ++x) cur[x] = (uint8_t)(line[x] + cur[x - bpp]);
-        break;
-      case 2:  // Up
-        if (prev)
-          for (int64_t x = 0; x < stride; ++x) cur[x] = (uint8_t)(line[x] + prev[x]);
-        else
-          memcpy(cur, line, (size_t)stride);
-        break;
-      case 3:  // Average
-        for (int64_t x = 0; x < head; ++x) cur[x] = (uint8_t)(line[x] + ((prev ? prev[x] : 0) >> 1));
-        for (int64_t x = head; x < stride; ++x) cur[x] = (uint8_t)(line[x] + ((cur[x - bpp] + (prev ? prev[x] : 0)) >> 1));
-        break;
-      case 4:  // Paeth
-        for (int64_t x = 0; x < head; ++x) cur[x] = (uint8_t)(line[x] + (prev ? prev[x] : 0));  // a = c = 0: the predictor is b
-        for (int64_t x = head; x < stride; ++x) {
-          const int a = cur[x - bpp], b = prev ? prev[x] : 0, c = prev ? prev[x - bpp] : 0;
-          const int pp = a + b - c;
-          const int pa = pp > a ? pp - a : a - pp, pb = pp > b ? pp - b : b - pp, pc = pp > c ? pp - c : c - pp;
-          const int pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-          cur[x] = (uint8_t)(line[x] + pred);
-        }
-        break;
-      default:
-        return fail(nullptr, SPK_ERR_PARSE, "spk_png_unfilter: filter type %d in row %lld", f, (long long)y);
-    }
-    prev = cur;
-  }
-  return SPK_OK;
-}
-
 }  // extern "C"

@@ -50,3 +50,28 @@ def read_gray(path):
     if chans >= 3 and not (np.array_equal(img[..., 0], img[..., 1]) and np.array_equal(img[..., 0], img[..., 2])):
         raise ValueError(f"{path}: colour PNG; IFCB ROI images are grayscale")
     return np.ascontiguousarray(img[..., 0])
+
+
+def read_gray_many(paths, threads=0):
+    """A sample's ROI images -> (w int32[n], h int32[n], start int64[n], data uint8[sum w*h]): the byte-stream layout of a
+    `.roi` file, decoded by the C-ABI host library on `threads` threads (0 = all cores, at most 16).  Python threads do not
+    help here (measured: 14.7 k ROI/s on one thread, 10 k on four -- the interpreter lock between the small numpy steps)."""
+    import ctypes as C
+
+    paths = [str(p) for p in paths]
+    n = len(paths)
+    w = np.empty(n, np.int32)
+    h = np.empty(n, np.int32)
+    if n == 0:
+        return w, h, np.empty(0, np.int64), np.empty(0, np.uint8)
+    lib = _lib.load()
+    arr = (C.c_char_p * n)(*[p.encode() for p in paths])
+    bad = C.c_int64(-1)
+    if lib.spk_png_probe(arr, n, w.ctypes.data, h.ctypes.data, threads, C.byref(bad)) != 0:
+        raise ValueError(_lib.last_error())
+    area = w.astype(np.int64) * h
+    start = np.concatenate([[0], np.cumsum(area)[:-1]]).astype(np.int64)
+    data = np.empty(int(area.sum()), np.uint8)
+    if lib.spk_png_decode_batch(arr, n, w.ctypes.data, h.ctypes.data, start.ctypes.data, data.ctypes.data, data.size, threads, C.byref(bad)) != 0:
+        raise ValueError(_lib.last_error())
+    return w, h, start, data

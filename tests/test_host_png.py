@@ -161,3 +161,89 @@ def test_process_images_decodes_in_order(tmp_path):
     assert csv_path.read_text() == "sentinel"
     probability.process_images([tmp_path / f"{sample}_{ids[0]:05d}.png"], Net(), params, csv_path, force=True)
     assert csv_path.read_text().startswith("roi,a,b\n7,")
+
+
+@pytest.mark.parametrize("threads", [1, 3, 0])
+def test_batch_decoder_matches_per_file_decoder(tmp_path, threads):
+    rng = np.random.default_rng(11)
+    paths, imgs = [], []
+    for k in range(60):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 120))
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        p = tmp_path / f"S_{k:05d}.png"
+        if k % 3 == 0:
+            write_png_up(p, img)
+        elif k % 3 == 1:
+            write_png(p, img[: min(h, 12), : min(w, 40)], [4, 3, 1, 2, 0])
+            img = img[: min(h, 12), : min(w, 40)]
+        else:  # gray stored as RGB / RGBA
+            c = 3 if k % 2 else 4
+            small = img[: min(h, 10), : min(w, 30)]
+            multi = np.repeat(small[..., None], c, axis=2)
+            write_png(p, multi, [1, 4], 2 if c == 3 else 6)
+            img = small
+        paths.append(p)
+        imgs.append(np.ascontiguousarray(img))
+    w, h, start, data = png.read_gray_many(paths, threads)
+    assert w.tolist() == [i.shape[1] for i in imgs] and h.tolist() == [i.shape[0] for i in imgs]
+    assert start.tolist() == np.concatenate([[0], np.cumsum([i.size for i in imgs])[:-1]]).tolist()
+    for k, img in enumerate(imgs):
+        got = data[start[k]: start[k] + img.size].reshape(img.shape)
+        assert np.array_equal(got, img) and np.array_equal(png.read_gray(paths[k]), img), k
+    assert png.read_gray_many([])[3].size == 0
+
+
+def test_batch_decoder_matches_cv2(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    paths = []
+    for k in range(50):
+        w, h = int(rng.integers(8, 500)), int(rng.integers(4, 260))
+        img = synth.synth_roi_pixels(rng, w, h) if k % 2 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+        p = tmp_path / f"D20210523T000000_IFCB114_{k:05d}.png"
+        assert cv2.imwrite(str(p), img, [cv2.IMWRITE_PNG_COMPRESSION, int(k % 10)])
+        paths.append(p)
+    w, h, start, data = png.read_gray_many(paths)
+    for k, p in enumerate(paths):
+        ref = cv2.imread(str(p))
+        assert ref.shape[:2] == (h[k], w[k])
+        assert np.array_equal(data[start[k]: start[k] + int(w[k]) * int(h[k])].reshape(h[k], w[k]), ref[..., 1])
+
+
+def test_batch_decoder_errors_name_the_file(tmp_path):
+    rng = np.random.default_rng(13)
+    good = []
+    for k in range(4):
+        p = tmp_path / f"S_{k:05d}.png"
+        write_png_up(p, rng.integers(0, 256, (9, 14), dtype=np.uint8))
+        good.append(p)
+    # missing file
+    with pytest.raises(ValueError, match="S_00009.png.*cannot open"):
+        png.read_gray_many(good + [tmp_path / "S_00009.png"])
+    # flipped payload byte: CRC error, as libpng / cv2.imread would refuse it
+    bad = tmp_path / "S_00005.png"
+    data = bytearray(good[0].read_bytes())
+    data[data.index(b"IDAT") + 9] ^= 0x55
+    bad.write_bytes(bytes(data))
+    with pytest.raises(ValueError, match="S_00005.png.*CRC"):
+        png.read_gray_many(good[:2] + [bad] + good[2:])
+    # colour image
+    col = tmp_path / "S_00006.png"
+    write_png(col, rng.integers(0, 256, (5, 7, 3), dtype=np.uint8), [0], ctype=2)
+    with pytest.raises(ValueError, match="S_00006.png.*colour"):
+        png.read_gray_many([col])
+    # not a PNG, 16-bit PNG
+    (tmp_path / "S_00007.png").write_bytes(b"GIF89a" + bytes(40))
+    with pytest.raises(ValueError, match="not a PNG"):
+        png.read_gray_many([tmp_path / "S_00007.png"])
+    hdr16 = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", 4, 4, 16, 0, 0, 0, 0)) + _chunk(b"IEND", b"")
+    (tmp_path / "S_00008.png").write_bytes(hdr16)
+    with pytest.raises(ValueError, match="unsupported PNG"):
+        png.read_gray_many([tmp_path / "S_00008.png"])
+    # truncated image data
+    w, h = 7, 5
+    stream = b"".join(b"\x00" + bytes(range(w)) for _ in range(h))[:-3]
+    short = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)) + _chunk(b"IDAT", zlib.compress(stream)) + _chunk(b"IEND", b"")
+    (tmp_path / "S_00010.png").write_bytes(short)
+    with pytest.raises(ValueError, match="bytes of image data"):
+        png.read_gray_many([tmp_path / "S_00010.png"])
