@@ -9,7 +9,7 @@ Prints one JSON line: ROIs/s (single thread unless --threads) of
   validate       spk_rois_validate (the geometry checks the reference performs implicitly)
   csv_format     spk_format_prob_csv, 50 classes (replaces probabilities_to_csv, compute/probability.py:200-206)
   csv_write      the formatted text to a file (tmpfs)
-  png_decode     png.read_gray of the same ROIs written as PNG files (image mode)
+  png_decode     png.read_gray per file / png.read_gray_many (the image mode's batch call, --threads C threads)
 and, for scale, what the reference's own Python does for the first and the last (str.split per line; f-string per value)."""
 import argparse
 import json
@@ -120,7 +120,8 @@ def main():
         p = pdir / f"{names[0]}_{int(i):05d}.png"
         write_png_up(p, bins[0]["roi_bytes"][int(s): int(s) + int(ww) * int(hh)].reshape(int(hh), int(ww)))
         paths.append(p)
-    res["png_decode"] = rate(png.read_gray, paths, len(paths), th)
+    res["png_decode"] = rate(png.read_gray, paths, len(paths), 1)  # one file at a time (Python container parsing + C filters)
+    res["png_decode_batch"] = rate(lambda _: png.read_gray_many(paths, th), [0], len(paths), 1)  # the image mode's call
     line = {"tool": "host_stages", "unit": "ROIs/s", "threads": th, "host_cpus": os.cpu_count(), "bins": args.bins, "rois": n_rois,
             "mean_roi_bytes": roi_bytes / n_rois, "csv_bytes_per_roi": len(csv[0]) / len(parsed[0][0]),
             "roi_read_gb_s": res["roi_read"] * roi_bytes / n_rois / 1e9, **{k: round(v) for k, v in res.items()}}
