@@ -22,6 +22,7 @@ and one host thread per GPU, no collective -- SURVEY.md 8e).
 import os
 import threading
 from collections import namedtuple
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
@@ -124,9 +125,18 @@ def main(
         net, params = make_params(devices[0])
         try:
             items = list(sample_paths.items())
-            for sample, img_paths in _progress(items, progress_bar):
-                csv_path = Path(out_dir) / f"{sample}{FILE_SUFFIX}.csv"
-                process_images(img_paths, net, params, csv_path, force)
+            csv_of = lambda sample: Path(out_dir) / f"{sample}{FILE_SUFFIX}.csv"  # noqa: E731
+            # the next sample's files are decoded (host library threads, no interpreter lock) while this one is on the GPU
+            with ThreadPoolExecutor(1) as pool:
+                def ahead(i):
+                    if i < len(items) and (force or not csv_of(items[i][0]).is_file()):
+                        return pool.submit(decode_images, items[i][1])
+                    return None
+
+                nxt = ahead(0)
+                for i, (sample, img_paths) in enumerate(_progress(items, progress_bar)):
+                    cur, nxt = nxt, ahead(i + 1)
+                    process_images(img_paths, net, params, csv_of(sample), force, decoded=cur.result() if cur else None)
         finally:
             net.close()
         return None
@@ -292,10 +302,11 @@ def process_sample(sample_path, net, params, out_dir, force=False):
     return sample
 
 
-def process_images(img_paths, net, params, csv_path, force=False):
+def process_images(img_paths, net, params, csv_path, force=False, decoded=None):
     """`--image-dir` / `--images` mode: ROIs come from PNG files named <sample>_<roi>.png
     (probability.py:165-177, :190).  The PNGs are decoded on the host (gray, as cv2.imread's three
-    equal planes) and packed into one byte stream, then take the same device path as a raw bin."""
+    equal planes) and packed into one byte stream, then take the same device path as a raw bin.
+    `decoded`: the result of `decode_images(img_paths)` if the caller already has it (main decodes one sample ahead)."""
     csv_path = Path(csv_path)
     if csv_path.is_file():
         if force:
@@ -303,17 +314,23 @@ def process_images(img_paths, net, params, csv_path, force=False):
         else:
             log.warning(f"{csv_path.name} already exists, skipping")
             return
-    from .. import png
-
-    # all files of the sample -> one byte stream (the layout of a `.roi` file), decoded by the host library's threads
-    img_paths = list(img_paths)
-    ids = np.array([int(Path(p).stem.split("_")[-1]) for p in img_paths], np.int32)
-    w, h, start, data = png.read_gray_many(img_paths)
+    ids, w, h, start, data = decoded if decoded is not None else decode_images(img_paths)
     if len(ids):
         probs = net.run_rois(ids, w, h, start, data, batch_size=params.batch_size)
         _write_csv(ids, probs, params.classes, csv_path)  # sorted by ROI id there (probability.py:197)
     else:
         probabilities_to_csv([], params.classes, csv_path)
+
+
+def decode_images(img_paths):
+    """All PNG files of a sample -> (roi ids, w, h, start, data): one byte stream laid out like a `.roi` file, decoded by
+    the host library's threads (sykepic_b200/png.py).  ROI id = last `_` field of the file stem (probability.py:190)."""
+    from .. import png
+
+    img_paths = list(img_paths)
+    ids = np.array([int(Path(p).stem.split("_")[-1]) for p in img_paths], np.int32)
+    w, h, start, data = png.read_gray_many(img_paths)
+    return ids, w, h, start, data
 
 
 def net_pass(net, rois, device=None, batch_size=None):

@@ -2,6 +2,7 @@
 against cv2.imread, which is what the reference uses (sykepic/train/data.py:217-219), and against hand-filtered files
 that force each of the five scanline filters."""
 import struct
+from pathlib import Path
 import zlib
 
 import numpy as np
@@ -247,3 +248,64 @@ def test_batch_decoder_errors_name_the_file(tmp_path):
     (tmp_path / "S_00010.png").write_bytes(short)
     with pytest.raises(ValueError, match="bytes of image data"):
         png.read_gray_many([tmp_path / "S_00010.png"])
+
+
+def test_main_image_mode_with_stand_in_engine(tmp_path, monkeypatch):
+    """`probability.main(..., samples_as_images=True)`: one CSV per sample directly under OUT (probability.py:96), the next
+    sample decoded while the current one runs, existing CSVs skipped (no decode either), engine closed at the end."""
+    from sykepic_b200.compute import probability
+
+    class Spec:
+        classes = ["a", "b"]
+        img_shape = (3, 64, 64)
+
+    class Eng:
+        instances = []
+
+        def __init__(self, spec, device=None, precision=None, max_batch=None):
+            self.device, self.calls, self.closed = "cpu", [], False
+            Eng.instances.append(self)
+
+        def run_rois(self, ids, w, h, start, data, batch_size=None):
+            self.calls.append(ids.tolist())
+            first = np.array([data[int(s)] for s in start], np.float32) / 255.0
+            return np.stack([first, 1.0 - first], axis=1).astype(np.float32)
+
+        def close(self):
+            self.closed = True
+
+    monkeypatch.setattr(probability._engine, "Engine", Eng)
+    monkeypatch.setattr(probability._engine.ModelSpec, "from_dir", classmethod(lambda cls, d: Spec()))
+    monkeypatch.setattr(probability, "_devices", lambda d: [0])
+    decoded = []
+    real_decode = probability.decode_images
+    monkeypatch.setattr(probability, "decode_images", lambda paths: decoded.append(Path(list(paths)[0]).name.rpartition("_")[0]) or real_decode(paths))
+
+    rng = np.random.default_rng(21)
+    samples = {}
+    for s in range(3):
+        name = f"D2021052{s}T000000_IFCB114"
+        paths = []
+        for i in (3, 1, 2):
+            p = tmp_path / f"{name}_{i:05d}.png"
+            write_png_up(p, rng.integers(0, 256, (6 + i, 10 + s), dtype=np.uint8))
+            paths.append(p)
+        samples[name] = sorted(paths)
+    out = tmp_path / "out"
+    out.mkdir()
+    names = list(samples)
+    (out / f"{names[1]}.prob.csv").write_text("sentinel")
+    assert probability.main(samples, tmp_path / "model", out, progress_bar=False, samples_as_images=True) is None
+    eng = Eng.instances[-1]
+    assert eng.closed and eng.calls == [[1, 2, 3], [1, 2, 3]]
+    assert decoded == [names[0], names[2]]  # the skipped sample is not even decoded
+    assert (out / f"{names[1]}.prob.csv").read_text() == "sentinel"
+    for nm in (names[0], names[2]):
+        lines = (out / f"{nm}.prob.csv").read_text().splitlines()
+        assert lines[0] == "roi,a,b" and [l.split(",")[0] for l in lines[1:]] == ["1", "2", "3"]
+        first = png.read_gray(samples[nm][0])[0, 0] / 255.0
+        assert abs(float(lines[1].split(",")[1]) - first) < 1e-5
+    # --force: all three
+    decoded.clear()
+    probability.main(samples, tmp_path / "model", out, force=True, progress_bar=False, samples_as_images=True)
+    assert decoded == names and (out / f"{names[1]}.prob.csv").read_text().startswith("roi,a,b")
