@@ -144,3 +144,31 @@ def test_threshold_quantize_is_the_decimal_comparison():
                 value = float(f"{cand / 1e5:.5f}")  # what pandas reads back from the CSV
                 above = value > t if strict else value >= t
                 assert above == (cand >= q), (t, strict, q, cand)
+
+
+def test_adc_parse_agrees_with_python_int_on_random_fields():
+    """Fields 15-17 go through Python's int() in the reference (utils/ifcb.py:104-106): optional whitespace, sign, digits with
+    single underscores.  Random strings over that alphabet (plus letters and dots) either parse to the same numbers or fail in both."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    field = st.text(alphabet=" \t+-_0123456789.a", min_size=0, max_size=8)
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.lists(st.tuples(field, field, field), min_size=1, max_size=4), st.sampled_from(["\n", "\r\n"]))
+    def check(rows, nl):
+        text = nl.join(",".join(["0"] * 15 + list(r) + ["x"] * 6) for r in rows) + nl
+        try:
+            want = o_ifcb.parse_adc_text(text)
+        except (ValueError, IndexError):
+            want = None
+        try:
+            rid, w, h, start = engine.parse_adc(text)
+            got = list(zip(rid.tolist(), w.tolist(), h.tolist(), start.tolist()))
+        except ValueError:
+            got = None
+        if want is not None and any(abs(v) >= 2 ** 31 for r in want for v in r[1:3]):
+            return  # widths beyond int32: Python's ints are unbounded, the C ABI reports a parse error
+        assert got == want, (text, got, want)
+
+    check()
