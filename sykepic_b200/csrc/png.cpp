@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -48,7 +49,8 @@ bool parse_ihdr(const unsigned char* d, size_t n, PngHeader* hd, std::string* er
     *err = b;
     return false;
   }
-  if (hd->w == 0 || hd->h == 0 || hd->w > (1u << 20) || hd->h > (1u << 20)) {
+  // (an IFCB ROI is at most 1380 x 1034; the cap keeps a forged header from asking for gigabytes)
+  if (hd->w == 0 || hd->h == 0 || hd->w > 65535u || hd->h > 65535u || (uint64_t)hd->w * hd->h * (uint64_t)hd->chans > (1ull << 28)) {
     *err = "bad image size";
     return false;
   }
@@ -222,7 +224,13 @@ int64_t parallel_first_bad(int64_t n, int threads, std::string* err, F&& job) {
       const int64_t i = next.fetch_add(1);
       if (i >= n || i > first_bad.load()) return;
       std::string e;
-      if (!job(i, &e)) {
+      bool ok = false;
+      try {
+        ok = job(i, &e);
+      } catch (const std::exception& ex) {  // nothing may unwind through a thread or the C ABI
+        e = ex.what();
+      }
+      if (!ok) {
         if (i < bad_idx[(size_t)t]) {
           bad_idx[(size_t)t] = i;
           errs[(size_t)t] = e;

@@ -309,3 +309,11 @@ def test_main_image_mode_with_stand_in_engine(tmp_path, monkeypatch):
     decoded.clear()
     probability.main(samples, tmp_path / "model", out, force=True, progress_bar=False, samples_as_images=True)
     assert decoded == names and (out / f"{names[1]}.prob.csv").read_text().startswith("roi,a,b")
+
+
+def test_forged_header_is_refused_not_allocated(tmp_path):
+    for w, h in [(60000, 60000), (2 ** 31, 1), (0, 5)]:
+        p = tmp_path / "S_00001.png"
+        p.write_bytes(b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 0, 0, 0, 0)) + _chunk(b"IDAT", zlib.compress(b"\x00")) + _chunk(b"IEND", b""))
+        with pytest.raises(ValueError, match="bad image size"):
+            png.read_gray_many([p])
