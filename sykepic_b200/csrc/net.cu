@@ -13,6 +13,8 @@
 #include <cstring>
 #include <memory>
 
+#include <exception>
+
 #include "spk_internal.h"
 
 namespace spk {
@@ -146,9 +148,18 @@ static void fold_bn(int c, const float* g, const float* b, const float* m, const
 
 using namespace spk;
 
+// No C++ exception may cross the C ABI (include/sykepic_b200.h): every entry point that allocates is a function-try-block.
+#define SPK_ABI_CATCH(ctx_, name_)                                                                       \
+  catch (const std::exception& e) {                                                                      \
+    return fail(ctx_, SPK_ERR_STATE, name_ ": %s", e.what());                                            \
+  }                                                                                                      \
+  catch (...) {                                                                                          \
+    return fail(ctx_, SPK_ERR_STATE, name_ ": unknown C++ exception");                                   \
+  }
+
 extern "C" {
 
-int spk_create(int device, void* stream, spk_ctx** out) {
+int spk_create(int device, void* stream, spk_ctx** out) try {
   if (!out) return fail(nullptr, SPK_ERR_INVALID, "spk_create: null out");
   *out = nullptr;
   int count = 0;
@@ -179,9 +190,9 @@ int spk_create(int device, void* stream, spk_ctx** out) {
   }
   *out = ctx.release();
   return SPK_OK;
-}
+} SPK_ABI_CATCH(nullptr, "spk_create")
 
-int spk_destroy(spk_ctx* ctx) {
+int spk_destroy(spk_ctx* ctx) try {
   if (!ctx) return SPK_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -195,33 +206,33 @@ int spk_destroy(spk_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   delete ctx;
   return SPK_OK;
-}
+} SPK_ABI_CATCH(nullptr, "spk_destroy")
 
-int spk_set_stream(spk_ctx* ctx, void* stream) {
+int spk_set_stream(spk_ctx* ctx, void* stream) try {
   if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_set_stream: null context");
   ctx->stream = (cudaStream_t)stream;
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_set_stream")
 
-int spk_synchronize(spk_ctx* ctx) {
+int spk_synchronize(spk_ctx* ctx) try {
   if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_synchronize: null context");
   SPK_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_synchronize")
 
 int64_t spk_launch_count(const spk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int spk_fault_count(spk_ctx* ctx, int64_t* count) {
+int spk_fault_count(spk_ctx* ctx, int64_t* count) try {
   if (!ctx || !count) return fail(ctx, SPK_ERR_INVALID, "spk_fault_count: bad arguments");
   unsigned long long v = 0;
   SPK_CUDA_OK(ctx, cudaMemcpyAsync(&v, ctx->d_faults, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
   SPK_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   *count = (int64_t)v;
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_fault_count")
 
 // ---------------------------------------------------------------------------------------- graph
-int spk_net_begin(spk_ctx* ctx, int target_h, int target_w, int in_channels, int precision, int max_batch) {
+int spk_net_begin(spk_ctx* ctx, int target_h, int target_w, int in_channels, int precision, int max_batch) try {
   if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_net_begin: null context");
   if (target_h < 1 || target_w < 1 || max_batch < 1) return fail(ctx, SPK_ERR_INVALID, "spk_net_begin: bad sizes");
   if (in_channels != 1 && in_channels != 3) return fail(ctx, SPK_ERR_UNSUPPORTED, "spk_net_begin: in_channels %d", in_channels);
@@ -249,9 +260,9 @@ int spk_net_begin(spk_ctx* ctx, int target_h, int target_w, int in_channels, int
   // the 256-entry LUT); 3 channels: fp32 NHWC as the reference tensor holds it.
   b0->dtype = in_channels == 1 ? SPK_DTYPE_U8 : SPK_DTYPE_F32;
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_begin")
 
-int spk_net_buffer(spk_ctx* ctx, int buf, int h, int w, int channels) {
+int spk_net_buffer(spk_ctx* ctx, int buf, int h, int w, int channels) try {
   int rc = need_net(ctx, true, "spk_net_buffer");
   if (rc) return rc;
   if (buf < 1 || h < 1 || w < 1 || channels < 1) return fail(ctx, SPK_ERR_INVALID, "spk_net_buffer: bad arguments");
@@ -260,11 +271,11 @@ int spk_net_buffer(spk_ctx* ctx, int buf, int h, int w, int channels) {
   define_buf(ctx->net, b, h, w, channels);
   b->declared = true;
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_buffer")
 
 int spk_net_conv(spk_ctx* ctx, int in_buf, int in_c_off, int out_buf, int out_c_off, int res_buf, const float* weight,
                  int cout, int cin, int kh, int kw, int stride, int pad, const float* bn_gamma, const float* bn_beta,
-                 const float* bn_mean, const float* bn_var, float bn_eps, const float* bias, int relu, int impl) {
+                 const float* bn_mean, const float* bn_var, float bn_eps, const float* bias, int relu, int impl) try {
   int rc = need_net(ctx, true, "spk_net_conv");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -348,9 +359,9 @@ int spk_net_conv(spk_ctx* ctx, int in_buf, int in_c_off, int out_buf, int out_c_
   op.impl = impl;
   net->ops.push_back(std::move(op));
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_conv")
 
-int spk_net_maxpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride, int pad) {
+int spk_net_maxpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride, int pad) try {
   int rc = need_net(ctx, true, "spk_net_maxpool");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -381,9 +392,9 @@ int spk_net_maxpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride, in
   op.g.wo = wo;
   net->ops.push_back(std::move(op));
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_maxpool")
 
-int spk_net_avgpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride) {
+int spk_net_avgpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride) try {
   int rc = need_net(ctx, true, "spk_net_avgpool");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -416,10 +427,10 @@ int spk_net_avgpool(spk_ctx* ctx, int in_buf, int out_buf, int k, int stride) {
   op.g.ldy = bo->c;
   net->ops.push_back(std::move(op));
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_avgpool")
 
 int spk_net_bn_relu(spk_ctx* ctx, int in_buf, int out_buf, int channels, const float* bn_gamma, const float* bn_beta,
-                    const float* bn_mean, const float* bn_var, float bn_eps, int relu) {
+                    const float* bn_mean, const float* bn_var, float bn_eps, int relu) try {
   int rc = need_net(ctx, true, "spk_net_bn_relu");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -453,10 +464,10 @@ int spk_net_bn_relu(spk_ctx* ctx, int in_buf, int out_buf, int channels, const f
   if (rc) return rc;
   net->ops.push_back(std::move(op));
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_bn_relu")
 
 int spk_net_head(spk_ctx* ctx, int in_buf, int n_layers, const float* const* weights, const float* const* biases,
-                 const int* dims) {
+                 const int* dims) try {
   int rc = need_net(ctx, true, "spk_net_head");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -502,9 +513,9 @@ int spk_net_head(spk_ctx* ctx, int in_buf, int n_layers, const float* const* wei
   net->feat = F;
   net->classes = K;
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_head")
 
-int spk_net_end(spk_ctx* ctx) {
+int spk_net_end(spk_ctx* ctx) try {
   int rc = need_net(ctx, true, "spk_net_end");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -724,13 +735,13 @@ int spk_net_end(spk_ctx* ctx) {
   }
   net->ended = true;
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_end")
 
 int64_t spk_net_bytes(const spk_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->bytes : 0; }
 
 // ---------------------------------------------------------------------------------------- forward
 int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, const int32_t* thr_q, float* probs,
-                int32_t* label, uint8_t* classified) {
+                int32_t* label, uint8_t* classified) try {
   int rc = need_net(ctx, false, "spk_forward");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -845,11 +856,11 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
                  "head pool %dx%d f=%d k=%d n=%d", bh.h, bh.w, net->feat, net->classes, (int)n);
   return launch_head(ctx, bh.d, bh.dtype, n, bh.h * bh.w, net->feat, net->d_head_w, net->d_head_b, net->classes,
                      softmax_scale, thr_q, net->d_logits, probs, label, classified);
-}
+} SPK_ABI_CATCH(ctx, "spk_forward")
 
 const float* spk_last_logits(const spk_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->d_logits : nullptr; }
 
-int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64_t cap_elems, int* h, int* w, int* c) {
+int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64_t cap_elems, int* h, int* w, int* c) try {
   int rc = need_net(ctx, false, "spk_net_read_buffer");
   if (rc) return rc;
   Net* net = ctx->net;
@@ -883,6 +894,6 @@ int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64
     }
   }
   return SPK_OK;
-}
+} SPK_ABI_CATCH(ctx, "spk_net_read_buffer")
 
 }  // extern "C"
