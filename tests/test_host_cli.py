@@ -1,0 +1,56 @@
+"""`python -m sykepic_b200 prob|class`: the reference's flags, defaults and exclusivity (sykepic/__main__.py:63-99, 134-190)."""
+import re
+from pathlib import Path
+
+import pytest
+
+from sykepic_b200.__main__ import build_parser
+
+REF_MAIN = Path("/root/reference/sykepic/__main__.py")
+
+
+def _sub(parser, name):
+    for a in parser._actions:
+        if getattr(a, "choices", None) and name in a.choices:
+            return a.choices[name]
+    raise AssertionError(name)
+
+
+def test_prob_flags_and_defaults():
+    p = build_parser()
+    a = p.parse_args(["prob", "-r", "RAW", "-m", "MODEL", "-o", "OUT"])
+    assert (a.raw, a.samples, a.image_dir, a.images, a.model, a.out) == ("RAW", None, None, None, "MODEL", "OUT")
+    assert (a.batch_size, a.num_workers, a.force) == (64, 2, False)
+    a = p.parse_args(["prob", "--samples", "a", "b", "-m", "M", "-o", "O", "-b", "256", "-w", "8", "-f"])
+    assert a.samples == ["a", "b"] and (a.batch_size, a.num_workers, a.force) == (256, 8, True)
+    assert p.parse_args(["prob", "--image-dir", "D", "-m", "M", "-o", "O"]).image_dir == "D"
+    assert p.parse_args(["prob", "--images", "x.png", "y.png", "-m", "M", "-o", "O"]).images == ["x.png", "y.png"]
+    for bad in (["prob", "-m", "M", "-o", "O"],  # one input source is required
+                ["prob", "-r", "R", "--image-dir", "D", "-m", "M", "-o", "O"],  # ... and only one
+                ["prob", "-r", "R", "-o", "O"], ["prob", "-r", "R", "-m", "M"]):
+        with pytest.raises(SystemExit):
+            p.parse_args(bad)
+
+
+def test_class_flags_and_defaults():
+    p = build_parser()
+    a = p.parse_args(["class", "PROBS", "-t", "THR", "-o", "out.csv"])
+    assert (a.probabilities, a.thresholds, a.out, a.feat, a.divisions) == ("PROBS", "THR", "out.csv", None, None)
+    assert (a.value_column, a.append, a.force) == ("biomass_ugl", False, False)
+    a = p.parse_args(["class", "P", "--feat", "F", "-t", "T", "-d", "DIV", "-o", "o.csv", "-v", "volume", "-a", "-f", "-exc", "EX"])
+    assert (a.feat, a.divisions, a.value_column, a.append, a.force, a.exclusion_list) == ("F", "DIV", "volume", True, True, "EX")
+    for bad in (["class", "P", "-o", "o.csv"], ["class", "P", "-t", "T"], ["class", "-t", "T", "-o", "o.csv"]):
+        with pytest.raises(SystemExit):
+            p.parse_args(bad)
+
+
+@pytest.mark.skipif(not REF_MAIN.is_file(), reason="the reference checkout is only present in the build container")
+def test_every_option_string_of_the_reference_is_accepted():
+    text = REF_MAIN.read_text()
+    parser = build_parser()
+    for sub, var in (("prob", r"prob_(?:parser|raw)"), ("class", r"class_parser")):
+        ours = set(_sub(parser, sub)._option_string_actions)
+        theirs = set()
+        for m in re.finditer(var + r"\.add_argument\((.*?)\)", text, re.S):
+            theirs |= set(re.findall(r'"(--?[A-Za-z][\w-]*)"', m.group(1)))
+        assert theirs and theirs <= ours, (sub, sorted(theirs - ours))
