@@ -197,6 +197,19 @@ int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64
  * strict = 1: smallest q with value > thr                                    (scalar threshold, prediction.py:58-59) */
 int32_t spk_threshold_quantize(double thr, int strict);
 
+/* ---- A10: reading a `.prob.csv` back (host) ------------------------------------------------
+ * `sykepic class` and every downstream tool re-read the probability files with pandas.read_csv inside
+ * prediction_dataframe (compute/prediction.py:8-28); at 5000 x 50 values per bin that read is 3/4 of the time of
+ * `sykepic class`.  These two calls parse the text as written by spk_format_prob_csv / probabilities_to_csv:
+ * a header line, then "<integer>,<decimal>,...".  Decimals are converted exactly as pandas' default parser
+ * does for them (correctly rounded: digits / 10^k in one IEEE division; plain decimals of up to 15 digits only).
+ *   spk_prob_csv_shape   rows (blank lines skipped) and value columns (header fields - 1)
+ *   spk_prob_csv_parse   roi[n_rows], values[n_rows * n_cols] (row-major doubles)
+ * SPK_ERR_PARSE on anything that is not this layout (quotes, ragged rows, non-numeric tokens): the caller then
+ * falls back to pandas, which decides as the reference would. */
+int spk_prob_csv_shape(const char* text, int64_t len, int64_t* n_rows, int* n_cols);
+int spk_prob_csv_parse(const char* text, int64_t len, int64_t n_rows, int n_cols, int64_t* roi, double* values);
+
 /* ---- image mode: PNG scanline filters (host) ----------------------------------------------
  * `sykepic prob --image-dir / --images` (compute/probability.py:28-36,165-177) reads ROI
  * images with cv2.imread (train/data.py:217-219).  Here the PNG container and zlib stream are

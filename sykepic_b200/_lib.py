@@ -85,6 +85,8 @@ PROTOTYPES = {
     "spk_net_read_buffer": (_i, [_p, _i, _i64, _p, _i64, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "spk_threshold_quantize": (C.c_int32, [C.c_double, _i]),
     "spk_format_prob_csv": (_i, [C.c_char_p, _p, _p, _i64, _i, _p, _i64, C.POINTER(_i64)]),
+    "spk_prob_csv_shape": (_i, [C.c_char_p, _i64, C.POINTER(_i64), C.POINTER(_i)]),
+    "spk_prob_csv_parse": (_i, [C.c_char_p, _i64, _i64, _i, _p, _p]),
     "spk_png_unfilter": (_i, [_p, _i64, _i64, _i, _p]),
     "spk_png_probe": (_i, [_p, _i64, _p, _p, _i, C.POINTER(_i64)]),
     "spk_png_decode_batch": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, C.POINTER(_i64)]),

@@ -16,17 +16,49 @@ import numpy as np
 import pandas as pd
 
 
+def read_prob_csv(csv, index_col=None):
+    """`pd.read_csv(csv)` / `pd.read_csv(csv, index_col=0)` for a `.prob.csv`, through the C-ABI host parser
+    (`spk_prob_csv_parse`: same float64 values as pandas' default parser -- correctly rounded -- at a tenth of the time;
+    pandas.read_csv is 3/4 of `sykepic class`).  Anything that is not the plain `roi,<class>,...` layout, an empty file, or a
+    missing library goes to pandas itself."""
+    try:
+        import ctypes as C
+
+        from .. import _lib
+
+        lib = _lib.load()
+        data = Path(csv).read_bytes()
+        n_rows, n_cols = C.c_int64(), C.c_int()
+        if lib.spk_prob_csv_shape(data, len(data), C.byref(n_rows), C.byref(n_cols)) != 0 or n_rows.value == 0 or n_cols.value < 1:
+            raise ValueError
+        header = data[: data.index(b"\n") if b"\n" in data else len(data)].rstrip(b"\r").decode("utf-8")
+        names = header.split(",")
+        if len(names) != n_cols.value + 1 or len(set(names)) != len(names) or any(n != n.strip() or not n for n in names):
+            raise ValueError  # duplicate / padded / empty names: pandas renames or strips them its own way
+        roi = np.empty(n_rows.value, np.int64)
+        values = np.empty((n_rows.value, n_cols.value), np.float64)
+        if lib.spk_prob_csv_parse(data, len(data), n_rows.value, n_cols.value, roi.ctypes.data, values.ctypes.data) != 0:
+            raise ValueError
+    except Exception:
+        return pd.read_csv(csv, index_col=index_col)
+    if index_col == 0:
+        return pd.DataFrame(values, index=pd.Index(roi, name=names[0]), columns=names[1:])
+    df = pd.DataFrame(values, columns=names[1:])
+    df.insert(0, names[0], roi)
+    return df
+
+
 def prediction_dataframe(probabilities, thresholds=0.0):
     if isinstance(probabilities, list):
         df_list = []
         for csv in probabilities:
-            df = pd.read_csv(csv)
+            df = read_prob_csv(csv)
             df.insert(0, "sample", Path(csv).with_suffix("").stem)
             df.set_index(["sample", "roi"], inplace=True)
             df_list.append(df)
         df = pd.concat(df_list)
     elif isinstance(probabilities, (str, Path)):
-        df = pd.read_csv(probabilities, index_col=0)
+        df = read_prob_csv(probabilities, index_col=0)
     else:
         raise ValueError(f"Type {type(probabilities)} not allowed for probabilities")
     if isinstance(thresholds, (str, Path)):

@@ -294,4 +294,97 @@ int spk_format_prob_csv(const char* header_line, const int32_t* roi_id, const fl
   return SPK_OK;
 }
 
+namespace {
+// one line of text [b, e) without its line terminator; false at the end of the text
+inline bool next_line(const char*& cur, const char* end, const char*& b, const char*& e) {
+  if (cur >= end) return false;
+  b = cur;
+  const char* nl = (const char*)memchr(cur, '\n', (size_t)(end - cur));
+  e = nl ? nl : end;
+  cur = nl ? nl + 1 : end;
+  if (e > b && e[-1] == '\r') --e;
+  return true;
+}
+const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                           1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+// [sign] digits [. digits] with at most 15 significant digits: mantissa and power of ten are both exact doubles, so one
+// division is the correctly rounded value (what pandas' default parser returns for such text, checked for all 100001
+// five-decimal values in tests/test_host_probcsv.py).  Nothing else is accepted.
+bool parse_decimal(const char* b, const char* e, double* out) {
+  const char* p = b;
+  bool neg = false;
+  if (p < e && (*p == '-' || *p == '+')) neg = (*p++ == '-');
+  uint64_t mant = 0;
+  int digits = 0, frac = 0;
+  bool dot = false, any = false;
+  for (; p < e; ++p) {
+    if (*p >= '0' && *p <= '9') {
+      any = true;
+      if (mant || *p != '0') ++digits;
+      if (digits > 15) break;
+      mant = mant * 10 + (uint64_t)(*p - '0');
+      if (dot) ++frac;
+    } else if (*p == '.' && !dot) {
+      dot = true;
+    } else {
+      break;
+    }
+  }
+  if (p == e && any && frac <= 22) {
+    const double v = (double)mant / kPow10[frac];
+    *out = neg ? -v : v;
+    return true;
+  }
+  return false;  // exponents, inf / nan, longer mantissas: not what the writers produce -- the caller lets pandas decide
+}
+}  // namespace
+
+int spk_prob_csv_shape(const char* text, int64_t len, int64_t* n_rows, int* n_cols) {
+  if (!text || len < 0 || !n_rows || !n_cols) return fail(nullptr, SPK_ERR_INVALID, "spk_prob_csv_shape: bad argument");
+  const char *cur = text, *end = text + len, *b, *e;
+  if (!next_line(cur, end, b, e) || b == e) return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_shape: no header line");
+  if (memchr(b, '"', (size_t)(e - b))) return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_shape: quoted header");
+  int fields = 1;
+  for (const char* p = b; p < e; ++p) fields += *p == ',';
+  int64_t rows = 0;
+  while (next_line(cur, end, b, e))
+    if (b != e) ++rows;  // pandas skips blank lines
+  *n_rows = rows;
+  *n_cols = fields - 1;
+  return SPK_OK;
+}
+
+int spk_prob_csv_parse(const char* text, int64_t len, int64_t n_rows, int n_cols, int64_t* roi, double* values) {
+  if (!text || len < 0 || n_rows < 0 || n_cols < 0 || (n_rows > 0 && (!roi || (n_cols > 0 && !values))))
+    return fail(nullptr, SPK_ERR_INVALID, "spk_prob_csv_parse: bad argument");
+  const char *cur = text, *end = text + len, *b, *e;
+  if (!next_line(cur, end, b, e)) return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_parse: no header line");
+  int64_t row = 0;
+  while (next_line(cur, end, b, e)) {
+    if (b == e) continue;
+    if (row >= n_rows) return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_parse: more rows than announced");
+    const char* p = b;
+    // the ROI id: plain digits (what both writers produce)
+    int64_t id = 0;
+    int nd = 0;
+    for (; p < e && *p >= '0' && *p <= '9' && nd < 18; ++p, ++nd) id = id * 10 + (*p - '0');
+    if (nd == 0 || (p < e && *p != ',') || (p == e && n_cols > 0))
+      return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_parse: line %lld: bad ROI id", (long long)(row + 2));
+    roi[row] = id;
+    for (int c = 0; c < n_cols; ++c) {
+      if (p >= e || *p != ',') return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_parse: line %lld: %d values expected", (long long)(row + 2), n_cols);
+      ++p;
+      const char* q = (const char*)memchr(p, ',', (size_t)(e - p));
+      if (!q) q = e;
+      if (!parse_decimal(p, q, &values[row * n_cols + c]))
+        return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_parse: line %lld, value %d is not a number", (long long)(row + 2), c + 1);
+      p = q;
+    }
+    if (p != e) return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_parse: line %lld: more than %d values", (long long)(row + 2), n_cols);
+    ++row;
+  }
+  if (row != n_rows) return fail(nullptr, SPK_ERR_PARSE, "spk_prob_csv_parse: fewer rows than announced");
+  return SPK_OK;
+}
+
 }  // extern "C"
