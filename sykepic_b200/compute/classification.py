@@ -27,76 +27,83 @@ NODU_COILED_BIG_BV = 36431
 NODU_COILED_BV_THRESHOLD = 200000
 
 
-def main(args):
-    all_probs = sorted(Path(args.probabilities).glob("**/*.csv"))
-    if getattr(args, "exclusion_list", None):
-        probs = filter_out_quality_flagged_samples(all_probs, Path(args.exclusion_list))
-    else:
-        probs = all_probs
-    out_file = Path(args.out)
-    if out_file.suffix != ".csv":
+def _output_target(args):
+    """The summary file and whether it is appended to.  The reference's rules (classification.py:28-33): the name must end
+    in `.csv`; an existing file needs --append or --force."""
+    target = Path(args.out)
+    if target.suffix != ".csv":
         raise ValueError("Make sure output file ends with .csv")
-    if out_file.is_file():
-        if not (args.append or args.force):
-            raise FileExistsError(f"{args.out} exists, --append or --force not used")
-    if getattr(args, "feat", None):
-        feats = sorted(Path(args.feat).glob("**/*.csv"))
-        df = class_df(probs, feats, thresholds_file=args.thresholds, divisions_file=getattr(args, "divisions", None),
-                      summary_feature=getattr(args, "value_column", None) or "biomass_ugl", progress_bar=True)
+    exists = target.is_file()
+    if exists and not (args.append or args.force):
+        raise FileExistsError(f"{args.out} exists, --append or --force not used")
+    return target, bool(args.append) and exists
+
+
+def main(args):
+    """`sykepic class` (argparse namespace): every `*.csv` under `probabilities`, minus quality-flagged samples, ->
+    one summary row per bin, written to `--out`."""
+    target, appending = _output_target(args)
+    prob_files = sorted(Path(args.probabilities).glob("**/*.csv"))
+    flagged = getattr(args, "exclusion_list", None)
+    if flagged:
+        prob_files = filter_out_quality_flagged_samples(prob_files, Path(flagged))
+    feat_root = getattr(args, "feat", None)
+    if feat_root:
+        table = class_df(prob_files, sorted(Path(feat_root).glob("**/*.csv")), thresholds_file=args.thresholds,
+                         divisions_file=getattr(args, "divisions", None),
+                         summary_feature=getattr(args, "value_column", None) or "biomass_ugl", progress_bar=True)
     else:
-        df = class_df_probs_only(probs, args.thresholds, progress_bar=True)
-    df = swell_df(df)
-    df_to_csv(df, out_file, args.append)
+        table = class_df_probs_only(prob_files, args.thresholds, progress_bar=True)
+    table = swell_df(table)
+    table.to_csv(target, mode="a" if appending else "w", header=not appending)
 
 
 def class_df_probs_only(probs, thresholds_file, progress_bar=False):
-    """One row per bin: number of classified ROIs per predicted class (threshold-file order) + Total."""
+    """One row per bin: number of classified ROIs per predicted class (threshold-file order) + `Total` = all ROIs."""
     thresholds = threshold_dictionary(thresholds_file)
-    classes = list(thresholds.keys()) + ["Total"]
-    rows = []
-    iterator = probs
-    if progress_bar:
-        try:
-            from tqdm import tqdm
+    names = list(thresholds)
+    table = {}
+    for csv in _wrap(probs, progress_bar, f"Processing {len(probs)} samples"):
+        frame = prediction_dataframe(Path(csv), thresholds)
+        if "prediction" not in frame.columns:
+            continue  # an empty bin has no prediction column: the reference's groupby raises KeyError and the bin is dropped (:122-123)
+        kept = frame.loc[frame["classified"], "prediction"].astype(str).value_counts()
+        row = {name: int(kept.get(name, 0)) for name in names}
+        row["Total"] = len(frame)
+        table[_stem(csv)] = row
+    out = pd.DataFrame.from_dict(table, orient="index", columns=names + ["Total"], dtype=int)
+    out.index.name = "sample"
+    return out
 
-            iterator = tqdm(probs, desc=f"Processing {len(probs)} samples")
-        except ImportError:
-            pass
-    for prob in iterator:
-        prob = Path(prob)
-        sample = prob.with_suffix("").stem
-        try:
-            pdf = prediction_dataframe(prob, thresholds)
-            counts = pdf.groupby("prediction", observed=False)["classified"].sum()
-        except KeyError:
-            continue  # e.g. an empty bin (no 'prediction' column): silently skipped like the reference
-        counts.index.name = "class"
-        counts.loc["Total"] = len(pdf)
-        counts.name = sample
-        rows.append(counts)
-    df = pd.DataFrame(rows, columns=classes)
-    df.index.name = "sample"
-    df = df.fillna(0)
-    return df.astype(int)
+
+# summed into one extra column by swell_df (classification.py:143-149): the first class plus the two genus subtotals, in
+# this order -- with the biomass columns of the --feat branch the association of the floating-point sum shows in the
+# last printed digit
+CYANOBACTERIA = (
+    ("Aphanizomenon_flosaquae",),
+    ("Dolichospermum-Anabaenopsis", "Dolichospermum-Anabaenopsis_coiled"),
+    ("Nodularia_spumigena", "Nodularia_spumigena-coiled"),
+)
 
 
 def swell_df(df):
-    """Index -> ISO-8601 UTC timestamps named `Time`; adds `Filamentous cyanobacteria` before `Total`;
-    underscores -> spaces in the column names.  KeyError when the cyanobacteria classes are not among
-    the columns, like the reference (classification.py:143-149)."""
-    df.index = df.index.map(lambda x: sample_to_datetime(x, isoformat=True))
-    df.index.name = "Time"
-    doli_sum = df[["Dolichospermum-Anabaenopsis", "Dolichospermum-Anabaenopsis_coiled"]].sum(axis=1)
-    nodu_sum = df[["Nodularia_spumigena", "Nodularia_spumigena-coiled"]].sum(axis=1)
-    cyano_sum = df["Aphanizomenon_flosaquae"] + doli_sum + nodu_sum
-    df.insert(len(df.columns) - 1, "Filamentous cyanobacteria", cyano_sum)
-    df.columns = df.columns.str.replace("_", " ")
+    """Bin names -> ISO-8601 UTC timestamps (index `Time`); a `Filamentous cyanobacteria` column (the classes above)
+    just before `Total`; underscores in the column names become spaces.  KeyError when one of those classes is not a column,
+    like the reference."""
+    df.index = pd.Index([sample_to_datetime(name, isoformat=True) for name in df.index], name="Time")
+    subtotals = [df[list(group)].sum(axis=1) if len(group) > 1 else df[group[0]] for group in CYANOBACTERIA]
+    filamentous = subtotals[0]
+    for part in subtotals[1:]:
+        filamentous = filamentous + part
+    df.insert(df.shape[1] - 1, "Filamentous cyanobacteria", filamentous)
+    df.columns = [str(c).replace("_", " ") for c in df.columns]
     return df
 
 
 def df_to_csv(df, out_file, append=False):
-    append = append and Path(out_file).is_file()
-    df.to_csv(out_file, mode="a" if append else "w", header=not append)
+    """Writes (or, with `append` and an existing file, appends without a header) the summary table."""
+    extend = bool(append) and Path(out_file).is_file()
+    df.to_csv(out_file, header=not extend, mode="a" if extend else "w")
 
 
 # ---------------------------------------------------------------------- feature-joined branch (--feat)
@@ -220,10 +227,10 @@ def divide_row(row, divisions, column):
 
 
 def names_of_divisions(divisions):
-    names = []
-    for key, values in divisions.items():
-        values = sorted(values)
-        names.append(f"{key}_under_{values[0]}")
-        names.append(f"{key}_over_{values[-1]}")
-        names.extend(f"{key}_{lo}_{hi}" for lo, hi in zip(values, values[1:]))
-    return names
+    """Column names of the size classes: per class, below its smallest limit, above its largest, then every interval."""
+    out = []
+    for cls, limits in divisions.items():
+        cuts = sorted(limits)
+        out += [f"{cls}_under_{cuts[0]}", f"{cls}_over_{cuts[-1]}"]
+        out += [f"{cls}_{lo}_{hi}" for lo, hi in zip(cuts[:-1], cuts[1:])]
+    return out

@@ -48,41 +48,47 @@ def read_prob_csv(csv, index_col=None):
     return df
 
 
+def _frame_of_many(csv_files):
+    """Several bins in one frame, indexed by (sample, roi); the sample is the file name without `.prob.csv`."""
+    parts = []
+    for csv in csv_files:
+        part = read_prob_csv(csv)
+        part.insert(0, "sample", Path(csv).with_suffix("").stem)
+        parts.append(part.set_index(["sample", "roi"]))
+    return pd.concat(parts)
+
+
 def prediction_dataframe(probabilities, thresholds=0.0):
-    if isinstance(probabilities, list):
-        df_list = []
-        for csv in probabilities:
-            df = read_prob_csv(csv)
-            df.insert(0, "sample", Path(csv).with_suffix("").stem)
-            df.set_index(["sample", "roi"], inplace=True)
-            df_list.append(df)
-        df = pd.concat(df_list)
-    elif isinstance(probabilities, (str, Path)):
-        df = read_prob_csv(probabilities, index_col=0)
+    """One `.prob.csv` (path) or several (list of paths) -> probabilities with `prediction` / `classified` in front.
+    `thresholds`: a number, a {class: value} dict, or the path of a thresholds file."""
+    if isinstance(probabilities, (str, Path)):
+        frame = read_prob_csv(probabilities, index_col=0)
+    elif isinstance(probabilities, list):
+        frame = _frame_of_many(probabilities)
     else:
         raise ValueError(f"Type {type(probabilities)} not allowed for probabilities")
     if isinstance(thresholds, (str, Path)):
         thresholds = threshold_dictionary(thresholds)
-    if not df.empty:
-        insert_prediction(df, thresholds)
-    return df
+    if len(frame.index) and len(frame.columns):
+        insert_prediction(frame, thresholds)
+    return frame
 
 
 def threshold_dictionary(thresholds, default=None):
-    """`<class> <float>` per line (whitespace separated); a missing value needs `default`."""
-    thres_dict = {}
+    """Thresholds file -> {class: value}.  One `<class> <value>` per line, any whitespace between them; a line with the
+    class alone takes `default` (ValueError without one); a blank line is an IndexError, as in the reference."""
     with open(thresholds) as fh:
-        for line in fh:
-            fields = line.strip().split()
-            key = fields[0]
-            if len(fields) > 1:
-                value = float(fields[1])
-            elif default:
-                value = float(default)
-            else:
-                raise ValueError(f"Missing threshold for {key}, and no default value specified.")
-            thres_dict[key] = value
-    return thres_dict
+        entries = [line.split() for line in fh]
+    table = {}
+    for fields in entries:
+        name = fields[0]
+        if len(fields) >= 2:
+            table[name] = float(fields[1])
+        elif default:
+            table[name] = float(default)
+        else:
+            raise ValueError(f"Missing threshold for {name}, and no default value specified.")
+    return table
 
 
 def predict_array(values, classes, thresholds):

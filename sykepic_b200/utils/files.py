@@ -21,4 +21,8 @@ def list_sample_paths(root_dir, filter=None):
 
 
 def list_sample_csvs(root_dir, filter=None):
-    return [p for p in Path(root_dir).glob("**/*.csv") if not filter or p.with_suffix("").stem in filter]
+    """Every `**/*.csv` under root_dir; with `filter`, only the files of those samples (`<sample>.<kind>.csv`)."""
+    found = Path(root_dir).glob("**/*.csv")
+    if not filter:
+        return list(found)
+    return [csv for csv in found if csv.name.split(".")[0] in filter]
