@@ -41,43 +41,41 @@ EvalParams = namedtuple(
 DEFAULT_PRECISION = os.environ.get("SYKEPIC_PRECISION", "fp32")
 
 
+ROI_FILE_LIMIT = 1e9  # bins whose `.roi` is larger are not processed (probability.py:45-51)
+
+
+def _samples_from_images(img_files):
+    """{sample: [its image files]} -- the sample is the file name up to its last `_` (probability.py:28-36)."""
+    grouped = {}
+    for img in img_files:
+        grouped.setdefault(img.name.rpartition("_")[0], []).append(img)
+    return grouped
+
+
+def _samples_from_bins(sample_paths):
+    """The bins to process: those whose `.roi` is within ROI_FILE_LIMIT; the others are reported and left out."""
+    kept = []
+    for sample_path in sample_paths:
+        if sample_path.with_suffix(".roi").stat().st_size > ROI_FILE_LIMIT:
+            log.warning(f"{sample_path.name} is over 1G, skipping")
+        else:
+            kept.append(sample_path)
+    return kept
+
+
 def call(args):
-    """Entry point of `sykepic prob` (argparse namespace, or any object with the same attributes)."""
-    if getattr(args, "image_dir", None) or getattr(args, "images", None):
-        samples_as_images = True
-        if args.image_dir:
-            img_paths = sorted(Path(args.image_dir).rglob("*.png"))
-        else:
-            img_paths = sorted(Path(path) for path in args.images)
-        sample_paths = {}
-        for img_path in img_paths:
-            sample_paths.setdefault(img_path.name.rpartition("_")[0], []).append(img_path)
-        filtered = sample_paths
+    """Entry point of `sykepic prob` (argparse namespace, or any object with the same attributes): one of
+    `raw` (directory of bins) / `samples` (bin paths without suffix) / `image_dir` / `images` (ROI PNG files)."""
+    image_dir, images = getattr(args, "image_dir", None), getattr(args, "images", None)
+    as_images = bool(image_dir or images)
+    if as_images:
+        pngs = Path(image_dir).rglob("*.png") if image_dir else (Path(p) for p in images)
+        work = _samples_from_images(sorted(pngs))
     else:
-        samples_as_images = False
-        if getattr(args, "raw", None):
-            sample_paths = files.list_sample_paths(args.raw)
-        else:
-            sample_paths = [Path(path) for path in args.samples]
-        # bins whose .roi is over 1 GB are not processed (probability.py:45-51)
-        filtered = []
-        for sample_path in sample_paths:
-            if sample_path.with_suffix(".roi").stat().st_size <= 1e9:
-                filtered.append(sample_path)
-            else:
-                log.warning(f"{sample_path.name} is over 1G, skipping")
-    return main(
-        filtered,
-        args.model,
-        args.out,
-        args.batch_size,
-        args.num_workers,
-        args.force,
-        progress_bar=True,
-        samples_as_images=samples_as_images,
-        precision=getattr(args, "precision", None),
-        devices=getattr(args, "devices", None),
-    )
+        raw_dir = getattr(args, "raw", None)
+        work = _samples_from_bins(files.list_sample_paths(raw_dir) if raw_dir else [Path(p) for p in args.samples])
+    return main(work, args.model, args.out, args.batch_size, args.num_workers, args.force, progress_bar=True,
+                samples_as_images=as_images, precision=getattr(args, "precision", None), devices=getattr(args, "devices", None))
 
 
 def _devices(devices):

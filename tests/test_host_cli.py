@@ -54,3 +54,38 @@ def test_every_option_string_of_the_reference_is_accepted():
         for m in re.finditer(var + r"\.add_argument\((.*?)\)", text, re.S):
             theirs |= set(re.findall(r'"(--?[A-Za-z][\w-]*)"', m.group(1)))
         assert theirs and theirs <= ours, (sub, sorted(theirs - ours))
+
+
+def test_prob_call_hands_main_the_work_list(tmp_path, monkeypatch):
+    """`probability.call` (sykepic/compute/probability.py:22-64 of the reference): the four input modes -> what `main` gets."""
+    from types import SimpleNamespace
+
+    from sykepic_b200.compute import probability
+
+    seen = {}
+    monkeypatch.setattr(probability, "main", lambda *a, **k: seen.update(args=a, kw=k) or "done")
+    raw = tmp_path / "raw" / "2021" / "05"
+    raw.mkdir(parents=True)
+    for name, size in (("D20210523T000000_IFCB114", 10), ("D20210523T002000_IFCB114", 20)):
+        (raw / f"{name}.roi").write_bytes(bytes(size))
+        (raw / f"{name}.adc").write_text("")
+    base = dict(raw=None, samples=None, image_dir=None, images=None, model="M", out="O", batch_size=64, num_workers=2, force=False)
+    assert probability.call(SimpleNamespace(**{**base, "raw": str(tmp_path / "raw")})) == "done"
+    work = seen["args"][0]
+    assert sorted(p.name for p in work) == ["D20210523T000000_IFCB114", "D20210523T002000_IFCB114"] and all(p.suffix == "" for p in work)
+    assert seen["args"][1:] == ("M", "O", 64, 2, False) and seen["kw"]["samples_as_images"] is False and seen["kw"]["progress_bar"] is True
+    # explicit sample paths; a bin over the size limit is left out (probability.py:45-51)
+    monkeypatch.setattr(probability, "ROI_FILE_LIMIT", 15)
+    probability.call(SimpleNamespace(**{**base, "samples": [str(raw / "D20210523T000000_IFCB114"), str(raw / "D20210523T002000_IFCB114")]}))
+    assert [p.name for p in seen["args"][0]] == ["D20210523T000000_IFCB114"]
+    # image modes: grouped by sample, files sorted
+    imgs = tmp_path / "imgs" / "sub"
+    imgs.mkdir(parents=True)
+    for n in ("A_IFCB1_00002.png", "A_IFCB1_00001.png", "B_IFCB1_00007.png"):
+        (imgs / n).write_bytes(b"")
+    probability.call(SimpleNamespace(**{**base, "image_dir": str(tmp_path / "imgs")}))
+    work = seen["args"][0]
+    assert list(work) == ["A_IFCB1", "B_IFCB1"] and [p.name for p in work["A_IFCB1"]] == ["A_IFCB1_00001.png", "A_IFCB1_00002.png"]
+    assert seen["kw"]["samples_as_images"] is True
+    probability.call(SimpleNamespace(**{**base, "images": [str(imgs / "B_IFCB1_00007.png"), str(imgs / "A_IFCB1_00002.png")]}))
+    assert {k: [p.name for p in v] for k, v in seen["args"][0].items()} == {"A_IFCB1": ["A_IFCB1_00002.png"], "B_IFCB1": ["B_IFCB1_00007.png"]}
