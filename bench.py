@@ -79,9 +79,19 @@ def workload(args, seed, n_chunks, rois=None):
     return out
 
 
+BENCH_CASE = {"resnet18": "bench_r18", "resnet50": "bench_r50", "densenet121": "bench_d121"}
+
+
 def model_dir(args, root):
+    """The checkpoint of the parity case of this architecture (tests/cases.py BIG_CASES: seeded random-init weights,
+    BatchNorm statistics calibrated on synthetic ROIs, logit spread of a trained checkpoint), so that the network
+    benchmarked here is the one tests/test_gpu_bench_parity.py holds against the reference's own output."""
     from sykepic_b200 import synth
 
+    if args.arch in BENCH_CASE and args.target == 224:
+        from tests.cases import case_model_dir
+
+        return case_model_dir(BENCH_CASE[args.arch], root)
     return synth.write_model_dir(Path(root) / f"model_{args.arch}", arch=args.arch, t=args.target, head=(256, 128), seed=0,
                                  border="mode", imagenet_normalization=False, randomize_bn=True, logit_gain=8.0)
 
@@ -159,61 +169,151 @@ def cpu_port_rate(args, mdir, batches, budget_s, max_rois=4096, chunk=64):
     return done / t_used, done, torch.get_num_threads()
 
 
+def parity_check(args, mdir, chunk, lo, probs, label, n=64):
+    """The outputs of the last timed step against the oracle (checker only): `n` ROIs spread evenly over that batch.
+    The full gates (every ROI of 1200-ROI bins against the reference's own output) are tests/test_gpu_bench_parity.py."""
+    import torch
+
+    from oracle import network, pipeline
+
+    model = pipeline.prepare_model(mdir)
+    w, h, start, roi = chunk
+    pick = np.unique(np.linspace(0, len(probs) - 1, n).astype(int))
+    imgs = [roi[start[lo + k]:start[lo + k] + int(w[lo + k]) * int(h[lo + k])].reshape(int(h[lo + k]), int(w[lo + k])) for k in pick]
+    want = network.probabilities(network.forward_logits(model.state_dict, torch.from_numpy(pipeline.preprocess_rois(model, imgs)))).numpy()
+    err = np.abs(probs[pick] - want)
+    tol = 2e-2 if args.precision == "bf16" else 1e-4
+    top2 = np.sort(want, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 2 * tol
+    same = label[pick] == want.argmax(axis=1)  # thresholds 0.5 everywhere: the label is the arg max either way
+    return {"max_dp": float(err.max()), "mean_dp": float(err.mean()), "n": int(len(pick)), "tol": tol, "ok": bool(err.max() <= tol),
+            "argmax_agree": float(same.mean()), "argmax_agree_decided": float(same[decided].mean()) if decided.any() else None,
+            "against": "oracle (numpy cv2-exact transform + torch-CPU fp32 forward) on ROIs spread over the last timed batch"}
+
+
+def _import_reference():
+    """The UNMODIFIED reference from baseline/_ref (installed by baseline/install_ref.sh; git-ignored, travels to the GPU
+    box) -> its `sykepic.compute.probability` module, or None.  Shim of SURVEY 8c: `sykepic/utils/ifcb.py:9` imports an
+    unused `pytz`, absent from this image -- a dummy module is injected after pandas has been imported."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "sykepic" / "compute" / "probability.py").exists():
+        return None
+    import types
+
+    import pandas  # noqa: F401  (before the stub: pandas probes pytz itself)
+
+    sys.modules.setdefault("pytz", types.ModuleType("pytz")).timezone = lambda name: None
+    sys.path.insert(0, str(ref))
+    try:
+        from sykepic.compute import probability as ref_probability
+    except Exception as e:  # noqa: BLE001
+        print(f"bench.py: reference import failed ({type(e).__name__}: {e}); falling back to the oracle port", file=sys.stderr)
+        sys.path.remove(str(ref))
+        return None
+    return ref_probability
+
+
 def run_reference(args):
+    """CPU arm.  kind "reference": the reference's own `probability.main` (baseline/_ref) on bins written to local
+    disk -- .adc/.roi -> PNG round trip -> DataLoader workers -> torch-CPU fp32 forward -> CSV, its stock code path --
+    one bin of `batch` ROIs per step, all host cores (best effort: batch_size = batch, num_workers = min(16, cores)).
+    kind "port" (only when baseline/_ref is absent): the oracle restatement."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return 0
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference picks cuda:0 when it sees one (probability.py:127); this is the CPU arm
     import torch
 
     # all the host threads this process may use (torchrun sets OMP_NUM_THREADS=1 for its workers)
     try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+        cores = max(1, len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        cores = max(1, os.cpu_count() or 1)
+    torch.set_num_threads(cores)
     args.batch = args.batch or (256 if args.arch == "resnet18" else 512)
-    tmp = tempfile.mkdtemp(prefix="spk_bench_")
+    tmp = tempfile.mkdtemp(prefix="spk_bench_ref_")
     mdir = model_dir(args, tmp)
-    batches = workload(args, 2000, 1)
-    from oracle import network, pipeline
+    ref_probability = _import_reference()
+    config = {"workload": f"{args.arch} 3x{args.target}x{args.target} synthetic IFCB ROIs, batch {args.batch}",
+              "arch": args.arch, "batch": args.batch, "target": args.target}
+    if ref_probability is not None:
+        from sykepic_b200 import synth
 
-    model = pipeline.prepare_model(mdir)
-    w, h, start, roi = batches[0]
-    # a step of the CPU arm = a bounded sample (64 ROIs) of the batch, all host threads
-    sample = min(64, args.batch)
+        # a step = one bin of `batch` ROIs; the CPU reference does ~100-250 ROIs/s, so the run is bounded by a time budget
+        sample = min(args.batch, 256)
+        raw = Path(tmp) / "raw"
+        n_bins = max(args.warmup, 1) + max(args.steps, 1)
+        paths = []
+        for i in range(n_bins):
+            b = synth.synth_bin(2000 + i, int(sample * 1.01) + 8)
+            keep = np.flatnonzero(b["w"] > 0)[:sample]
+            area = b["w"][keep].astype(np.int64) * b["h"][keep]
+            start = np.concatenate([[0], np.cumsum(area)[:-1]]).astype(np.int64)
+            roi = np.concatenate([b["roi_bytes"][s:s + a] for s, a in zip(b["start"][keep], area)])
+            paths.append(synth.write_bin(raw, synth.bin_name(i), {"adc_text": synth.adc_text(b["w"][keep], b["h"][keep], start), "roi_bytes": roi}))
+        workers = min(16, cores)
+        out = Path(tmp) / "out"
+        nw = max(args.warmup, 1)
+        ref_probability.main(paths[:nw], mdir, out, batch_size=args.batch, num_workers=workers, force=True, progress_bar=False)
+        budget = 150.0
+        done = 0
+        t0 = time.perf_counter()
+        # one `main` call per slice of bins so that the time budget can end the run; model construction is inside (as in the CLI)
+        for i in range(nw, n_bins):
+            got = ref_probability.main(paths[i:i + 1], mdir, out, batch_size=args.batch, num_workers=workers, force=True, progress_bar=False)
+            assert got == {paths[i].name}, got
+            done += 1
+            if time.perf_counter() - t0 > budget:
+                break
+        dt = time.perf_counter() - t0
+        n_csv = len(list(out.glob("**/*.prob.csv")))
+        assert n_csv >= done
+        kind = "reference"
+        note = ("CPU arm: the reference's own sykepic.compute.probability.main from baseline/_ref (unmodified; stock path: PNG round "
+                f"trip, DataLoader with {workers} workers, torch-CPU fp32, CSV), one bin of {sample} ROIs per step, model built per call")
+        sample_txt = f"{done} steps x one bin of {sample} ROIs through probability.main (files -> CSV)"
+    else:
+        from oracle import network, pipeline
 
-    def step(i):
-        lo = (i * sample) % (len(w) - sample + 1)
-        imgs = [roi[start[k]:start[k] + int(w[k]) * int(h[k])].reshape(int(h[k]), int(w[k])) for k in range(lo, lo + sample)]
-        x = torch.from_numpy(pipeline.preprocess_rois(model, imgs))
-        with torch.no_grad():
-            network.probabilities(network.forward_logits(model.state_dict, x)).tolist()
+        batches = workload(args, 2000, 1)
+        model = pipeline.prepare_model(mdir)
+        w, h, start, roi = batches[0]
+        sample = min(64, args.batch)
 
-    steps = args.steps
-    for i in range(max(args.warmup, 1) if steps > 0 else 0):
-        step(i)
-    t0 = time.perf_counter()
-    budget = 150.0
-    done = 0
-    for i in range(steps):
-        step(i)
-        done += 1
-        if time.perf_counter() - t0 > budget:
-            break
-    dt = time.perf_counter() - t0
+        def step(i):
+            lo = (i * sample) % (len(w) - sample + 1)
+            imgs = [roi[start[k]:start[k] + int(w[k]) * int(h[k])].reshape(int(h[k]), int(w[k])) for k in range(lo, lo + sample)]
+            x = torch.from_numpy(pipeline.preprocess_rois(model, imgs))
+            with torch.no_grad():
+                network.probabilities(network.forward_logits(model.state_dict, x)).tolist()
+
+        for i in range(max(args.warmup, 1) if args.steps > 0 else 0):
+            step(i)
+        t0 = time.perf_counter()
+        done = 0
+        for i in range(args.steps):
+            step(i)
+            done += 1
+            if time.perf_counter() - t0 > 150.0:
+                break
+        dt = time.perf_counter() - t0
+        kind = "port"
+        note = "CPU arm: oracle port of the reference path (baseline/_ref is absent): numpy cv2-exact transform + torch-CPU fp32 forward"
+        sample_txt = f"{done} steps x {sample} ROIs of the batch"
     value = done * sample / dt
+    config["note"] = note
+    config["rois_per_step"] = sample
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.arch} 3x{args.target}x{args.target} synthetic IFCB ROIs, batch {args.batch}",
-                   "arch": args.arch, "batch": args.batch, "target": args.target,
-                   "note": "CPU arm: oracle port of the reference path (numpy cv2-exact transform + torch-CPU fp32 forward); "
-                           "the reference itself is Python and /root/reference does not travel to the GPU box"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{done} steps x {sample} ROIs of the batch", "host_cpus": os.cpu_count()},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_txt, "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+    import shutil
+
+    shutil.rmtree(tmp, ignore_errors=True)
     return 0
 
 
@@ -305,6 +405,11 @@ def run_b200(args):
     clocks = sampler.stop()
     gpu_launches = eng.launches - launches0
     assert eng.fault_count() == 0
+    # what the LAST timed step produced (checked against the oracle below, outside every timed region)
+    last = args.steps - 1
+    last_chunk, last_lo = (last // G) % n_pool, (last % G) * args.batch
+    last_probs = probs[last_lo:last_lo + args.batch].cpu().numpy()
+    last_label = label[last_lo:last_lo + args.batch].cpu().numpy()
 
     # ---- e2e: host API on whole chunks (a bin is what the API takes), pinned host buffers, H2D + D2H inside the timed region
     host_in = [(w, h, start, torch.from_numpy(roi).pin_memory().numpy()) for w, h, start, roi in chunks]
@@ -429,6 +534,7 @@ def run_b200(args):
             "kernel_ms_per_step": step_ms,
             "wall_s_timed_region": wall,
         }
+        line["parity"] = parity_check(args, mdir, chunks[last_chunk], last_lo, last_probs, last_label)
         if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only (under torchrun OMP_NUM_THREADS is 1)
             rate, n_done, cores = cpu_port_rate(args, mdir, chunks, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

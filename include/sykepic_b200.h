@@ -44,6 +44,8 @@ extern "C" {
 #define SPK_ERR_CAPACITY      -6  /* caller-provided output buffer too small */
 #define SPK_ERR_UNSUPPORTED   -7
 #define SPK_ERR_STATE         -8  /* call order violated (e.g. spk_forward before spk_net_end) */
+#define SPK_ERR_IO            -9  /* a file could not be opened / read / written (message has errno's text); the
+                                     reference raises OSError and logs "Unexpected error" for the bin */
 
 /* ---- enums -------------------------------------------------------------------------- */
 enum { SPK_BORDER_MODE = 0, SPK_BORDER_BLACK = 1, SPK_BORDER_WHITE = 2 }; /* sykepic/train/image.py:20-28 */
@@ -105,6 +107,16 @@ int spk_adc_parse(const char* text, int64_t len, int64_t cap,
  * offending ROI (or -1). */
 int spk_rois_validate(const int32_t* width, const int32_t* height, const int64_t* start, int64_t n,
                       int64_t roi_len, int target_h, int target_w, int64_t* first_bad);
+
+/* One bin from disk in a single call (the loader threads of the host pipeline spend their time here, outside the
+ * Python interpreter lock): read and parse `adc_path` (as spk_adc_parse), read `roi_path` straight into `roi_buf`
+ * (typically pinned host memory; *roi_len = the file's size, SPK_ERR_CAPACITY if it exceeds roi_cap -- *roi_len is
+ * set, retry with a larger buffer), then check the geometry (as spk_rois_validate).  Replaces the file reads of
+ * ifcb.raw_to_png (sykepic/utils/ifcb.py:76-118: `open(adc)`, `np.fromfile(roi)`).  SPK_ERR_IO when a file cannot
+ * be read. */
+int spk_bin_load(const char* adc_path, const char* roi_path, uint8_t* roi_buf, int64_t roi_cap, int64_t desc_cap,
+                 int32_t* roi_id, int32_t* width, int32_t* height, int64_t* start, int64_t* n_out, int64_t* roi_len,
+                 int target_h, int target_w);
 
 /* get_new_dims of sykepic/train/image.py:183-198 (float64 arithmetic, truncation). */
 void spk_new_dims(int h, int w, int target_h, int target_w, int* new_h, int* new_w);
@@ -171,6 +183,9 @@ int spk_net_head(spk_ctx* ctx, int in_buf, int n_layers, const float* const* wei
 int spk_net_end(spk_ctx* ctx);
 /* Bytes of device memory the network holds (weights + workspace). */
 int64_t spk_net_bytes(const spk_ctx* ctx);
+/* Convolution layers of a BF16 / FP32_TC network that SPK_CONV_AUTO had to place on the CUDA-core kernel because no
+ * tcgen05 kernel takes their geometry (0 for every torchvision ResNet / DenseNet; each one is also reported on stderr). */
+int spk_net_simt_layers(const spk_ctx* ctx);
 
 /* ---- A6/A8/A10: forward + softmax + per-class threshold (kernels K2, K3) ---------------
  * Replaces net_pass (compute/probability.py:180-197: logits * ln(1.3) in fp32, softmax)
@@ -238,6 +253,10 @@ int spk_png_decode_batch(const char* const* paths, int64_t n, const int32_t* wid
  * Writes at most cap bytes into out, *len = bytes needed. */
 int spk_format_prob_csv(const char* header_line, const int32_t* roi_id, const float* probs,
                         int64_t n, int k, char* out, int64_t cap, int64_t* len);
+/* The same text written to `path` (created / truncated; parent directories must exist) in one call: what
+ * probabilities_to_csv's `open(csv_path, "w")` + `write` do (probability.py:205-206).  SPK_ERR_IO on failure. */
+int spk_prob_csv_write(const char* path, const char* header_line, const int32_t* roi_id, const float* probs,
+                       int64_t n, int k, int64_t* bytes_written);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,9 @@
 """Builds libsykepic_b200.so (the C-ABI library) in-tree with nvcc for sm_100a.
 
-    python -m sykepic_b200._build [--force] [--verbose]
+    python -m sykepic_b200._build [--force] [--verbose] [--debug]
+
+`--debug` adds -DSPK_DEBUG_SWITCHES: the A/B and trace switches of tools/README.md are then read from the environment
+(csrc/spk_debug.h); the product build has them compiled out.
 
 Every translation unit is compiled with
 `-gencode arch=compute_100a,code=sm_100a -lineinfo` and linked (static cudart)
@@ -24,7 +27,7 @@ INCLUDE = ROOT / "include"
 BUILD = ROOT / "build" / "spk"
 LIB = PKG / "libsykepic_b200.so"
 
-SOURCES = ["host.cpp", "png.cpp", "net.cu", "preprocess.cu", "conv_simt.cu", "conv_tc.cu", "conv_halo.cu", "conv_pair.cu", "conv_hp.cu", "stem.cu", "stem_t.cu", "head.cu"]
+SOURCES = ["host.cpp", "png.cpp", "net.cu", "preprocess.cu", "conv_simt.cu", "conv_tc.cu", "conv_pair.cu", "conv_hp.cu", "stem.cu", "stem_t.cu", "head.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", f"-I{INCLUDE}", f"-I{CSRC}"]
@@ -45,8 +48,8 @@ def _digest(paths, extra=""):
     return h.hexdigest()
 
 
-def _compile(src, obj, verbose):
-    cmd = [nvcc(), *ARCH, *FLAGS, "-x", "cu", "-c", str(src), "-o", str(obj)]
+def _compile(src, obj, verbose, extra=()):
+    cmd = [nvcc(), *ARCH, *FLAGS, *extra, "-x", "cu", "-c", str(src), "-o", str(obj)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), flush=True)
@@ -57,12 +60,13 @@ def _compile(src, obj, verbose):
         raise RuntimeError(f"nvcc failed on {src.name}")
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
     """Compile (if stale) and return the path of the shared library."""
+    extra = ("-DSPK_DEBUG_SWITCHES",) if debug else ()
     BUILD.mkdir(parents=True, exist_ok=True)
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     headers = sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h"))
-    flags_key = " ".join(ARCH + FLAGS)
+    flags_key = " ".join(ARCH + FLAGS + list(extra))
     hdr_digest = _digest(headers, flags_key)
     jobs, objs = [], []
     for src in srcs:
@@ -74,7 +78,7 @@ def build(force=False, verbose=False):
             jobs.append((src, obj, stamp, want))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-            list(ex.map(lambda j: _compile(j[0], j[1], verbose), jobs))
+            list(ex.map(lambda j: _compile(j[0], j[1], verbose, extra), jobs))
         for _, _, stamp, want in jobs:
             stamp.write_text(want)
     if jobs or not LIB.exists():
@@ -87,4 +91,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, debug="--debug" in sys.argv))

@@ -19,6 +19,7 @@ SPK_ERR_PARSE = -5
 SPK_ERR_CAPACITY = -6
 SPK_ERR_UNSUPPORTED = -7
 SPK_ERR_STATE = -8
+SPK_ERR_IO = -9
 
 BORDER = {"mode": 0, "black": 1, "white": 2}
 DTYPE_F32, DTYPE_BF16, DTYPE_U8, DTYPE_SPLIT = 0, 1, 2, 3
@@ -67,6 +68,8 @@ PROTOTYPES = {
     "spk_profile_read": (_i, [_p, _p, _p, _p, _p, _p, _i64]),
     "spk_profile_end": (_i, [_p]),
     "spk_adc_parse": (_i, [C.c_char_p, _i64, _i64, _p, _p, _p, _p, C.POINTER(_i64), C.POINTER(_i64)]),
+    "spk_bin_load": (_i, [C.c_char_p, C.c_char_p, _p, _i64, _i64, _p, _p, _p, _p, C.POINTER(_i64), C.POINTER(_i64), _i, _i]),
+    "spk_prob_csv_write": (_i, [C.c_char_p, C.c_char_p, _p, _p, _i64, _i, C.POINTER(_i64)]),
     "spk_rois_validate": (_i, [_p, _p, _p, _i64, _i64, _i, _i, C.POINTER(_i64)]),
     "spk_new_dims": (None, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "spk_preprocess": (_i, [_p, _p, _i64, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _p]),
@@ -80,6 +83,7 @@ PROTOTYPES = {
     "spk_net_head": (_i, [_p, _i, _i, _pp, _pp, C.POINTER(_i)]),
     "spk_net_end": (_i, [_p]),
     "spk_net_bytes": (_i64, [_p]),
+    "spk_net_simt_layers": (_i, [_p]),
     "spk_forward": (_i, [_p, _p, _i64, _f, _p, _p, _p, _p]),
     "spk_last_logits": (_p, [_p]),
     "spk_net_read_buffer": (_i, [_p, _i, _i64, _p, _i64, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
@@ -126,6 +130,8 @@ def check(rc, ctx=None):
         raise EmptyResize(rc, msg)
     if rc == SPK_ERR_PARSE:
         raise AdcParseError(msg)
+    if rc == SPK_ERR_IO:
+        raise OSError(msg)
     raise SpkError(rc, msg)
 
 

@@ -89,7 +89,10 @@ def _devices(devices):
             devices = [int(os.environ.get("LOCAL_RANK", 0))] if torch.cuda.is_available() else [0]
     elif isinstance(devices, int):
         devices = list(range(devices))
-    return list(devices)
+    devices = list(devices)
+    if not devices:
+        raise ValueError("sykepic prob: at least one GPU is needed (devices / --gpus / SYKEPIC_DEVICES is empty or 0)")
+    return devices
 
 
 def main(
@@ -194,17 +197,40 @@ def main(
         for pr in procs:
             pr.start()
         failures = []
-        for _ in procs:
-            dev, done, err, stats = queue.get()
+        reported = set()
+        import queue as _queue
+
+        def take(msg):
+            dev, done, err, stats = msg
+            reported.add(dev)
             if err:
                 failures.append(f"GPU {dev}: {err}")
-            samples_processed |= set(done)
+            samples_processed.update(done)
             if stats:
                 from .. import pipeline
 
                 pipeline.LAST_STATS.append(stats)
             if bar is not None:
-                bar.update(len(done))
+                bar.update(len(shards[devices.index(dev)]))  # every bin of the shard: processed, skipped or failed
+
+        # A worker that dies without reporting (segfault, OOM kill, CUDA abort) must not hang the parent: poll the queue
+        # and watch the children; one that has exited without a message is recorded as a failure.
+        while len(reported) < len(procs):
+            try:
+                take(queue.get(timeout=1.0))
+                continue
+            except _queue.Empty:
+                pass
+            for dev, pr in zip(devices, procs):
+                if dev not in reported and not pr.is_alive():
+                    try:  # its message may have arrived between the time-out and the liveness check
+                        while True:
+                            take(queue.get_nowait())
+                    except _queue.Empty:
+                        pass
+                    if dev not in reported:
+                        reported.add(dev)
+                        failures.append(f"GPU {dev}: worker process exited with code {pr.exitcode} without reporting")
         for pr in procs:
             pr.join()
         if failures:
@@ -259,17 +285,6 @@ def _progress(items, progress_bar):
     except ImportError:
         return items
     return tqdm(items, desc="Processing samples")
-
-
-def _guarded(sample_path, net, params, out_dir, force, processed):
-    """Per-bin error policy of the reference (probability.py:106-114): log and carry on."""
-    sample_path = Path(sample_path)
-    try:
-        processed.add(process_sample(sample_path, net, params, out_dir, force))
-    except ValueError:
-        log.exception(f"Faulty raw data for {sample_path.name}")
-    except Exception:
-        log.exception(f"Unexpected error for {sample_path.name}:")
 
 
 def prepare_model(model_dir, precision=None, device=None, max_batch=256):

@@ -384,7 +384,7 @@ struct HpConvPlan {
 };
 
 bool hp_conv_supported(const ConvGeom& g) {
-  static const bool off = getenv("SPK_NO_HP") != nullptr;  // A/B switch
+  static const bool off = debug_env("SPK_NO_HP") != nullptr;  // A/B switch
   if (off) return false;
   if (g.kh != 3 || g.kw != 3 || g.stride != 1 || g.pad != 1) return false;
   if ((g.cout != 32 && g.cout != 64 && g.cout != 128) || (g.cin != 64 && g.cin != 128)) return false;
@@ -489,7 +489,7 @@ int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void
   prm.m_tiles = n * prm.tiles_h;
   prm.units = (prm.m_tiles + 1) / 2;
   const int clusters = std::min(prm.units, ctx->sm_count / 2);
-  static const bool want_trace = getenv("SPK_HP_TRACE") != nullptr;
+  static const bool want_trace = debug_env("SPK_HP_TRACE") != nullptr;
   static long long* d_trace = nullptr;
   static int trace_left = 6;
   prm.trace = nullptr;

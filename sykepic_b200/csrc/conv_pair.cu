@@ -371,7 +371,7 @@ struct PairConvPlan {
 };
 
 bool pair_conv_supported(const ConvGeom& g) {
-  static const bool off = getenv("SPK_NO_PAIR") != nullptr;  // A/B switch
+  static const bool off = debug_env("SPK_NO_PAIR") != nullptr;  // A/B switch
   if (off) return false;
   if (!tc_conv_supported(g)) return false;
   if (g.cout % 128 != 0 || g.cout > 4096) return false;
@@ -420,7 +420,7 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
   prm.tiles_h = (g.ho + prm.hb - 1) / prm.hb;
   // ---- N tile: 256 halves the A re-reads, but a layer with few M tiles (7x7 maps: 98 pairs x N tiles at batch 256) then
   // leaves most of the 74 clusters idle in its last round; pick the width with the shorter schedule at the planned batch
-  if (g.cout % 256 == 0 && !p->ds && getenv("SPK_PAIR_BN_AUTO")) {  // measured (512->512 @7x7, batch 256): 0.063 ms at N = 128 vs 0.058-0.062 at N = 256; off
+  if (g.cout % 256 == 0 && !p->ds && debug_env("SPK_PAIR_BN_AUTO")) {  // measured (512->512 @7x7, batch 256): 0.063 ms at N = 128 vs 0.058-0.062 at N = 256; off
     const long long m_tiles = (long long)prm.tiles_w * prm.tiles_h * ((g.n + prm.nb - 1) / prm.nb);
     const long long pairs = (m_tiles + 1) / 2, clusters = std::max(1, ctx->sm_count / 2);
     auto rounds = [&](int bn) { return (pairs * (g.cout / bn) + clusters - 1) / clusters; };
@@ -589,7 +589,7 @@ int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const 
   prm.m_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img;
   prm.units = ((prm.m_tiles + 1) / 2) * prm.tiles_n;
   const int clusters = std::min(prm.units, ctx->sm_count / 2);
-  static const bool want_trace = getenv("SPK_PAIR_TRACE") != nullptr;
+  static const bool want_trace = debug_env("SPK_PAIR_TRACE") != nullptr;
   static long long* d_trace = nullptr;
   static int trace_left = 4;
   prm.trace = nullptr;

@@ -1,9 +1,16 @@
 // Host-side entry points of the C ABI: context-free utilities (.adc parsing, geometry
 // validation, .prob.csv formatting, threshold quantisation).  No CUDA here.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 
 #include "spk_internal.h"
 
@@ -292,6 +299,103 @@ int spk_format_prob_csv(const char* header_line, const int32_t* roi_id, const fl
   *len = pos;
   if (out && pos > cap) return fail(nullptr, SPK_ERR_CAPACITY, "spk_format_prob_csv: need %lld bytes", (long long)pos);
   return SPK_OK;
+}
+
+// ---- whole-file helpers for the host pipeline (no interpreter lock is held while these run)
+namespace {
+struct Fd {
+  int fd = -1;
+  ~Fd() {
+    if (fd >= 0) close(fd);
+  }
+};
+// reads exactly `want` bytes (the caller sized the buffer from fstat); false on error / short file
+bool read_all(int fd, uint8_t* dst, int64_t want) {
+  int64_t got = 0;
+  while (got < want) {
+    const ssize_t r = read(fd, dst + got, (size_t)std::min<int64_t>(want - got, (int64_t)1 << 30));
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    if (r == 0) return false;
+    got += r;
+  }
+  return true;
+}
+}  // namespace
+
+int spk_bin_load(const char* adc_path, const char* roi_path, uint8_t* roi_buf, int64_t roi_cap, int64_t desc_cap,
+                 int32_t* roi_id, int32_t* width, int32_t* height, int64_t* start, int64_t* n_out, int64_t* roi_len,
+                 int target_h, int target_w) try {
+  if (!adc_path || !roi_path || !n_out || !roi_len || roi_cap < 0 || desc_cap < 0)
+    return fail(nullptr, SPK_ERR_INVALID, "spk_bin_load: bad arguments");
+  *n_out = 0;
+  *roi_len = 0;
+  // ---- .adc: read whole, parse
+  std::vector<char> adc;
+  {
+    Fd f;
+    f.fd = open(adc_path, O_RDONLY | O_CLOEXEC);
+    if (f.fd < 0) return fail(nullptr, SPK_ERR_IO, "%s: %s", adc_path, strerror(errno));
+    struct stat st;
+    if (fstat(f.fd, &st) != 0) return fail(nullptr, SPK_ERR_IO, "%s: %s", adc_path, strerror(errno));
+    adc.resize((size_t)st.st_size);
+    if (st.st_size > 0 && !read_all(f.fd, reinterpret_cast<uint8_t*>(adc.data()), (int64_t)st.st_size))
+      return fail(nullptr, SPK_ERR_IO, "%s: short read", adc_path);
+  }
+  int64_t n = 0, lines = 0;
+  int rc = spk_adc_parse(adc.empty() ? "" : adc.data(), (int64_t)adc.size(), desc_cap, roi_id, width, height, start, &n, &lines);
+  if (rc != SPK_OK) return rc;
+  // ---- .roi: straight into the caller's (pinned) buffer
+  Fd f;
+  f.fd = open(roi_path, O_RDONLY | O_CLOEXEC);
+  if (f.fd < 0) return fail(nullptr, SPK_ERR_IO, "%s: %s", roi_path, strerror(errno));
+  struct stat st;
+  if (fstat(f.fd, &st) != 0) return fail(nullptr, SPK_ERR_IO, "%s: %s", roi_path, strerror(errno));
+  *roi_len = (int64_t)st.st_size;
+  if ((int64_t)st.st_size > roi_cap)
+    return fail(nullptr, SPK_ERR_CAPACITY, "spk_bin_load: %s has %lld bytes, the buffer %lld", roi_path, (long long)st.st_size,
+                (long long)roi_cap);
+#ifdef POSIX_FADV_SEQUENTIAL
+  posix_fadvise(f.fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+  if (st.st_size > 0) {
+    if (!roi_buf) return fail(nullptr, SPK_ERR_INVALID, "spk_bin_load: null .roi buffer");
+    if (!read_all(f.fd, roi_buf, (int64_t)st.st_size)) return fail(nullptr, SPK_ERR_IO, "%s: short read", roi_path);
+  }
+  *n_out = n;
+  // ---- geometry: "Faulty raw data" / zero-pixel resize, as the reference finds out while decoding
+  int64_t bad = -1;
+  return spk_rois_validate(width, height, start, n, (int64_t)st.st_size, target_h, target_w, &bad);
+} catch (const std::exception& e) {
+  return fail(nullptr, SPK_ERR_STATE, "spk_bin_load: %s", e.what());
+}
+
+int spk_prob_csv_write(const char* path, const char* header_line, const int32_t* roi_id, const float* probs, int64_t n, int k,
+                       int64_t* bytes_written) try {
+  if (!path || !header_line || n < 0 || k < 0) return fail(nullptr, SPK_ERR_INVALID, "spk_prob_csv_write: bad arguments");
+  const int64_t cap = (int64_t)strlen(header_line) + n * (12 + 8 * (int64_t)k + 1) + 16;
+  std::vector<char> text((size_t)cap);
+  int64_t len = 0;
+  int rc = spk_format_prob_csv(header_line, roi_id, probs, n, k, text.data(), cap, &len);
+  if (rc != SPK_OK) return rc;
+  Fd f;
+  f.fd = open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0666);
+  if (f.fd < 0) return fail(nullptr, SPK_ERR_IO, "%s: %s", path, strerror(errno));
+  int64_t put = 0;
+  while (put < len) {
+    const ssize_t r = write(f.fd, text.data() + put, (size_t)(len - put));
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return fail(nullptr, SPK_ERR_IO, "%s: %s", path, strerror(errno));
+    }
+    put += r;
+  }
+  if (bytes_written) *bytes_written = len;
+  return SPK_OK;
+} catch (const std::exception& e) {
+  return fail(nullptr, SPK_ERR_STATE, "spk_prob_csv_write: %s", e.what());
 }
 
 namespace {

@@ -42,7 +42,6 @@ struct Op {
   float* d_pre_shift = nullptr;  // conv with a fused pre-activation (DenseNet BN + ReLU applied to the A tiles): shift
   int pre_c = 0, pre_relu = 0;
   TcConvPlan* tc = nullptr;
-  HaloConvPlan* halo = nullptr;
   HpConvPlan* hpair = nullptr;
   PairConvPlan* pair = nullptr;
   // fused downsample branch (1x1 / stride 2 of the same input, computed by this 3x3 / stride 2 convolution's kernel)
@@ -63,12 +62,12 @@ struct Net {
   std::vector<Op> ops;
   bool ended = false;
   bool has_head = false;
-  int early_end = 0, early_parts = 1;  // ops [0, early_end) run per slice of the batch (L2 residency), see spk_forward
   int head_in = -1, feat = 0, classes = 0;
   float* d_head_w = nullptr;  // [K][F]
   float* d_head_b = nullptr;
   float* d_logits = nullptr;  // [max_batch][K]
   int64_t bytes = 0;
+  int simt_layers = 0;  // convolutions of a tensor-core precision that had to take the CUDA-core kernel
 };
 
 static size_t dtype_size(int dt) { return (dt == SPK_DTYPE_F32 || dt == SPK_DTYPE_SPLIT) ? 4 : dt == SPK_DTYPE_BF16 ? 2 : 1; }
@@ -85,7 +84,6 @@ static void net_free(Net* net) {
     if (op.d_bias_ds) cudaFree(op.d_bias_ds);
     if (op.d_stem_w) cudaFree(op.d_stem_w);
     if (op.tc) tc_conv_plan_destroy(op.tc);
-    if (op.halo) halo_conv_plan_destroy(op.halo);
     if (op.hpair) hp_conv_plan_destroy(op.hpair);
     if (op.pair) pair_conv_plan_destroy(op.pair);
   }
@@ -563,7 +561,7 @@ int spk_net_end(spk_ctx* ctx) try {
   }
   // ---- downsample fusion: a ResNet block's 1x1 / stride-2 shortcut reads exactly the pixels the centre tap of the
   // block's 3x3 / stride-2 convolution reads; the pair becomes one launch with two accumulators
-  if (net->precision == SPK_PRECISION_BF16 && !getenv("SPK_NO_DS_FUSION")) {
+  if (net->precision == SPK_PRECISION_BF16 && !debug_env("SPK_NO_DS_FUSION")) {
     for (size_t i = 0; i + 1 < net->ops.size(); ++i) {
       Op& a = net->ops[i];      // the shortcut (the host declares it first)
       Op& b = net->ops[i + 1];  // the 3x3
@@ -584,7 +582,7 @@ int spk_net_end(spk_ctx* ctx) try {
   // ---- pre-activation fusion (DenseNet): bn_relu(concat[:, :c]) -> 1x1 convolution becomes one launch; the BatchNorm +
   // ReLU is applied to the convolution's A tiles in shared memory (conv_tc.cu, kModePre).  Only unpadded convolutions:
   // a padding pixel must stay 0, not relu(shift).
-  if (net->precision == SPK_PRECISION_BF16 && !getenv("SPK_NO_PRE_FUSION")) {
+  if (net->precision == SPK_PRECISION_BF16 && !debug_env("SPK_NO_PRE_FUSION")) {
     for (size_t i = 0; i + 1 < net->ops.size(); ++i) {
       Op& a = net->ops[i];      // bn_relu
       Op& b = net->ops[i + 1];  // its only consumer
@@ -633,7 +631,15 @@ int spk_net_end(spk_ctx* ctx) try {
                            : (split_in && tc_conv_split_supported(g));
     const bool taps_only = impl == SPK_CONV_TCGEN05_TAPS;
     if (taps_only) impl = SPK_CONV_TCGEN05;
-    if (impl == SPK_CONV_AUTO) impl = tc_ok ? SPK_CONV_TCGEN05 : SPK_CONV_SIMT;
+    if (impl == SPK_CONV_AUTO) {
+      impl = tc_ok ? SPK_CONV_TCGEN05 : SPK_CONV_SIMT;
+      if (!tc_ok && net->precision != SPK_PRECISION_FP32 && op.in != 0) {
+        // no silent 27x cliff: say which layer left the tensor cores (spk_net_simt_layers reports the count)
+        ++net->simt_layers;
+        fprintf(stderr, "spk: WARNING: convolution %dx%d/%d %d->%d on %dx%d has no tcgen05 kernel in this precision; it runs on CUDA cores\n",
+                g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w);
+      }
+    }
     if (impl == SPK_CONV_TCGEN05 && !tc_ok)
       return fail(ctx, SPK_ERR_UNSUPPORTED, "spk_net_end: tcgen05 convolution does not support %dx%d s%d cin %d cout %d here",
                   g.kh, g.kw, g.stride, g.cin, g.cout);
@@ -657,10 +663,6 @@ int spk_net_end(spk_ctx* ctx) try {
         rc = hp_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.hpair);
         if (rc) return rc;
         net->bytes += hp_conv_plan_bytes(op.hpair);
-      } else if (!taps_only && halo_conv_supported(gm)) {
-        rc = halo_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.halo);
-        if (rc) return rc;
-        net->bytes += halo_conv_plan_bytes(op.halo);
       } else if (!taps_only && op.ds_out < 0 && pair_conv_supported(gm)) {
         rc = pair_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.pair);
         if (rc) return rc;
@@ -668,7 +670,7 @@ int spk_net_end(spk_ctx* ctx) try {
       } else if (op.ds_out >= 0) {
         rc = upload(ctx, op.ds_b.data(), op.ds_b.size(), &op.d_bias_ds);
         if (rc) return rc;
-        if (!taps_only && pair_conv_supported(gm) && !getenv("SPK_NO_PAIR_DS")) {
+        if (!taps_only && pair_conv_supported(gm) && !debug_env("SPK_NO_PAIR_DS")) {
           rc = pair_conv_plan_create(ctx, gm, op.w_host.data(), op.d_bias, &op.pair, op.ds_w.data(), op.d_bias_ds, op.ds_ld);
           if (rc) return rc;
           net->bytes += pair_conv_plan_bytes(op.pair);
@@ -695,30 +697,8 @@ int spk_net_end(spk_ctx* ctx) try {
     std::vector<float>().swap(op.w_host);
     std::vector<float>().swap(op.b_host);
   }
-  // ---- early segment: the leading ops whose input or output map exceeds 16 MB per 64 images (ResNet: stem, layer1, first entry)
-  net->early_end = 0;
-  net->early_parts = 1;
-  if (net->precision == SPK_PRECISION_BF16 && !getenv("SPK_NO_EARLY_SPLIT")) {
-    size_t end = 0;
-    for (size_t i = 0; i < net->ops.size(); ++i) {
-      const Op& op = net->ops[i];
-      if (op.kind == kOpNop) continue;
-      if (op.kind != kOpConv && op.kind != kOpStemPool) break;  // (pool / bn_relu ops keep the whole batch: DenseNet)
-      const double in_mb = 64.0 * op.g.h * op.g.w * op.g.ldx * dtype_size(net->bufs[(size_t)op.in].dtype) / 1e6;
-      if (op.in != 0 && in_mb < 16.0) break;
-      end = i + 1;
-    }
-    // every buffer written in the segment must not be read across slices in a way that breaks: ops are per-image, so any
-    // prefix of the op list is valid as long as it ends on an op boundary
-    if (end >= 2 && end < net->ops.size()) {
-      net->early_end = (int)end;
-      const char* e = getenv("SPK_EARLY_PARTS");
-      net->early_parts = e ? std::max(1, atoi(e)) : 1;  // measured (ResNet-18, batch 256): 2 slices 0.988 ms vs 0.968 whole, 4 slices 1.061:
-                                                        // the per-launch overheads outweigh the L2 hits; off unless asked for
-    }
-  }
   // ---- L2-friendly traversal: launch k walks its tiles in the direction opposite to launch k-1 (the stem goes forward)
-  if (!getenv("SPK_NO_ZIGZAG")) {
+  if (!debug_env("SPK_NO_ZIGZAG")) {
     int dir = 0;
     for (auto& op : net->ops) {
       if (op.kind == kOpNop) continue;
@@ -727,7 +707,7 @@ int spk_net_end(spk_ctx* ctx) try {
         if (op.hpair) hp_conv_plan_set_reverse(op.hpair, dir);
         else if (op.pair) pair_conv_plan_set_reverse(op.pair, dir);
         else if (op.tc) tc_conv_plan_set_reverse(op.tc, dir);
-        else dir = 0;  // single-CTA halo kernel: forward only
+        else dir = 0;
       } else {
         dir = 0;  // every other kernel walks forward
       }
@@ -739,6 +719,8 @@ int spk_net_end(spk_ctx* ctx) try {
 
 int64_t spk_net_bytes(const spk_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->bytes : 0; }
 
+int spk_net_simt_layers(const spk_ctx* ctx) { return (ctx && ctx->net) ? ctx->net->simt_layers : 0; }
+
 // ---------------------------------------------------------------------------------------- forward
 int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, const int32_t* thr_q, float* probs,
                 int32_t* label, uint8_t* classified) try {
@@ -748,17 +730,13 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
   if (n == 0) return SPK_OK;
   if (!x || !probs || n < 0) return fail(ctx, SPK_ERR_INVALID, "spk_forward: null buffer");
   if (n > net->max_batch) return fail(ctx, SPK_ERR_CAPACITY, "spk_forward: batch %lld > max_batch %d", (long long)n, net->max_batch);
-  const int64_t n_all = n;
-  // ops [ob, oe) on images [n0, n0 + n) of the batch
-  auto run_ops = [&](size_t ob, size_t oe, int64_t n0, int64_t n) -> int {
-  int rc = SPK_OK;
-  // `img` = elements per image of the tensor as THIS op sees it (buffer ids are reused with different shapes)
-  auto ptr = [&](int id, int c_off, size_t img = 0) -> char* {
+  // channel offset `c_off` into buffer `id` (DenseNet concat slices); every op takes the whole batch
+  auto ptr = [&](int id, int c_off, size_t = 0) -> char* {
     Buffer& b = net->bufs[(size_t)id];
     char* base = id == 0 ? (char*)const_cast<void*>(x) : (char*)b.d;
-    return base + ((size_t)n0 * img + (size_t)c_off) * dtype_size(b.dtype);
+    return base + (size_t)c_off * dtype_size(b.dtype);
   };
-  for (size_t oi = ob; oi < oe; ++oi) {
+  for (size_t oi = 0; oi < net->ops.size(); ++oi) {
     Op& op = net->ops[oi];
     const Buffer& bi = net->bufs[(size_t)op.in];
     const Buffer& bo = net->bufs[(size_t)op.out];
@@ -773,13 +751,11 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
                        (double)n * g.h * g.w * g.cin * dtype_size(bi.dtype) + px * g.cout * dtype_size(bo.dtype) * ((op.res >= 0 ? 2 : 1) + ds_taps) +
                            (double)g.cout * (g.kh * g.kw + ds_taps) * g.cin * (op.impl == SPK_CONV_TCGEN05 ? 2 : 4),
                        "conv%dx%d/%d %d->%d in %dx%d out %dx%d n=%d%s%s%s", g.kh, g.kw, g.stride, g.cin, g.cout, g.h, g.w, g.ho,
-                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.hpair ? " [halo pair]" : op.halo ? " [halo]" : (op.pair ? (op.ds_out >= 0 ? " [pair +1x1/2 shortcut]" : " [pair]") : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : (op.pre_c > 0 ? " [bn+relu on A]" : ""))));
+                       g.wo, (int)n, op.res >= 0 ? " +res" : "", g.relu ? " relu" : "", op.hpair ? " [halo pair]" : (op.pair ? (op.ds_out >= 0 ? " [pair +1x1/2 shortcut]" : " [pair]") : (op.ds_out >= 0 ? " [+1x1/2 shortcut]" : (op.pre_c > 0 ? " [bn+relu on A]" : ""))));
         const size_t img_in = (size_t)g.h * g.w * g.ldx, img_out = (size_t)g.ho * g.wo * g.ldy;
         const void* res = op.res >= 0 ? ptr(op.res, 0, (size_t)g.ho * g.wo * g.ldres) : nullptr;
         if (op.hpair)
           rc = hp_conv_launch(ctx, op.hpair, (int)n, ptr(op.in, op.in_off, img_in), res, ptr(op.out, op.out_off, img_out));
-        else if (op.halo)
-          rc = halo_conv_launch(ctx, op.halo, (int)n, ptr(op.in, op.in_off, img_in), res, ptr(op.out, op.out_off, img_out));
         else if (op.pair)
           rc = pair_conv_launch(ctx, op.pair, (int)n, ptr(op.in, op.in_off, img_in), res, ptr(op.out, op.out_off, img_out),
                                 op.ds_out >= 0 ? ptr(op.ds_out, op.ds_off, (size_t)g.ho * g.wo * op.ds_ld) : nullptr);
@@ -831,25 +807,6 @@ int spk_forward(spk_ctx* ctx, const void* x, int64_t n, float softmax_scale, con
     }
     if (rc) return rc;
   }
-  return SPK_OK;
-  };
-  // The large early maps (stem, layer1, the first stage entry) are walked in slices of the batch so that what one kernel
-  // writes is still in the 126 MB L2 when the next one reads it (a 56x56x64 map of 256 images is 103 MB); the small late
-  // maps take the whole batch at once (their tile counts barely fill the GPU as it is).
-  const size_t n_ops = net->ops.size();
-  const int parts = (net->early_end > 0 && n >= 2 * 64) ? std::min<int64_t>(net->early_parts, n / 64) : 1;
-  if (parts > 1) {
-    const int64_t per = ((n + parts - 1) / parts + 1) & ~(int64_t)1;  // even, so that CTA pairs stay full
-    for (int64_t n0 = 0; n0 < n; n0 += per) {
-      rc = run_ops(0, (size_t)net->early_end, n0, std::min<int64_t>(per, n - n0));
-      if (rc) return rc;
-    }
-    rc = run_ops((size_t)net->early_end, n_ops, 0, n);
-  } else {
-    rc = run_ops(0, n_ops, 0, n);
-  }
-  if (rc) return rc;
-  n = n_all;
   const Buffer& bh = net->bufs[(size_t)net->head_in];
   ProfScope prof(ctx, SPK_PROF_HEAD, 2.0 * n * net->feat * net->classes,
                  (double)n * bh.h * bh.w * net->feat * dtype_size(bh.dtype) + (double)n * net->classes * 4,

@@ -15,6 +15,8 @@
 // pixel is written exactly once with 16-byte stores.
 #include <cooperative_groups.h>
 
+#include <exception>
+
 #include "spk_internal.h"
 
 namespace cg = cooperative_groups;
@@ -782,9 +784,10 @@ using namespace spk;
 
 extern "C" int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t roi_len, const int64_t* start,
                               const int32_t* width, const int32_t* height, int64_t n, int target_h, int target_w,
-                              int border_mode, int channels, int out_dtype, int out_layout, const float* lut, void* out) {
+                              int border_mode, int channels, int out_dtype, int out_layout, const float* lut, void* out) try {
   if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_preprocess: null context");
   if (n == 0) return SPK_OK;
+  SPK_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   if (!roi_bytes || !start || !width || !height || !out || n < 0)
     return fail(ctx, SPK_ERR_INVALID, "spk_preprocess: null buffer");
   if (target_h < 1 || target_w < 1 || target_h > kMaxTarget || target_w > kMaxTarget)
@@ -848,15 +851,23 @@ extern "C" int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t ro
     Params pb = p;
     pb.slabs = kBigSlabs;
     preprocess_big_kernel<<<kBigClusters * kBigSlabs, kThreads, kHBytes, ctx->stream2>>>(pb);
-    SPK_LAUNCH_CHECK(ctx);
-    SPK_CUDA_OK(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    const cudaError_t e_big = cudaGetLastError();
+    ctx->launches++;
+    // whatever happened on the side stream, the main stream joins it again before this call returns
+    const cudaError_t e_rec = cudaEventRecord(ctx->ev_join, ctx->stream2);
     p.slabs = n <= 2048 ? 4 : n <= 8192 ? 2 : 1;  // warps per ROI (fills the partial last wave of a bin-sized launch)
     const long long items = n * p.slabs;
     preprocess_u8_kernel<<<(unsigned)((items + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, 0, ctx->stream>>>(p, (long long)n);
-    SPK_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    const cudaError_t e_join = e_rec == cudaSuccess ? cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0) : e_rec;
+    if (e_big != cudaSuccess) return fail(ctx, SPK_ERR_CUDA, "spk_preprocess: cluster kernel launch: %s", cudaGetErrorString(e_big));
+    if (e_join != cudaSuccess) return fail(ctx, SPK_ERR_CUDA, "spk_preprocess: stream join: %s", cudaGetErrorString(e_join));
   } else {
     preprocess_kernel<<<(unsigned)blocks, kThreads, kHBytes, ctx->stream>>>(p);
   }
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;
+} catch (const std::exception& e) {
+  return fail(ctx, SPK_ERR_STATE, "spk_preprocess: %s", e.what());
+} catch (...) {
+  return fail(ctx, SPK_ERR_STATE, "spk_preprocess: unknown C++ exception");
 }

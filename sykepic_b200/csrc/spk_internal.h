@@ -12,6 +12,8 @@
 
 #include "sykepic_b200.h"
 
+#include "spk_debug.h"
+
 namespace spk {
 
 constexpr int kMaxTarget = 512;  // largest supported target side (T_h, T_w)
@@ -147,14 +149,6 @@ int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void
 int64_t tc_conv_plan_bytes(const TcConvPlan* p);
 // consecutive layers walk their tiles in alternating directions, so that a kernel starts on what the previous one left in L2
 void tc_conv_plan_set_reverse(TcConvPlan* p, int reverse);
-// conv_halo.cu (3x3 / stride 1: halo tile resident in shared memory, taps = shifted descriptors, TMA-store epilogue)
-struct HaloConvPlan;
-bool halo_conv_supported(const ConvGeom& g);
-int halo_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w_oihw_folded /*[Cout][kh][kw][cin] fp32*/,
-                          const float* bias, HaloConvPlan** out);
-void halo_conv_plan_destroy(HaloConvPlan* p);
-int halo_conv_launch(spk_ctx* ctx, HaloConvPlan* p, int n, const void* x, const void* res, void* y);
-int64_t halo_conv_plan_bytes(const HaloConvPlan* p);
 // conv_pair.cu (Cout >= 128: CTA pairs, tcgen05.mma.cta_group::2, each CTA stages half of the weight tile)
 struct PairConvPlan;
 bool pair_conv_supported(const ConvGeom& g);

@@ -483,7 +483,7 @@ bool stem_pool_supported(const ConvGeom& g, int pool_k, int pool_stride, int poo
 enum { kStemHilo = 0, kStemHalf = 1, kStemT = 2 };
 static int stem_variant(bool split) {
   static const int v = [] {
-    const char* e = getenv("SPK_STEM");
+    const char* e = debug_env("SPK_STEM");
     if (e && !strcmp(e, "hilo")) return (int)kStemHilo;
     if (e && !strcmp(e, "half")) return (int)kStemHalf;
     return (int)kStemT;
@@ -551,7 +551,7 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
   p.wp = wp;
   p.ldy = ldy;
   p.strips = (hp + kPoolRowsPerStrip - 1) / kPoolRowsPerStrip;
-  static const bool no_tma = getenv("SPK_STEM_NO_TMA") != nullptr;  // A/B switch: stage the strip with the builder threads
+  static const bool no_tma = debug_env("SPK_STEM_NO_TMA") != nullptr;  // A/B switch: stage the strip with the builder threads
   p.use_tma = (!no_tma && tw % 16 == 0 && tw <= 224 && ((uintptr_t)x & 15) == 0 && encode_fn() != nullptr) ? 1 : 0;
   p.groups = (tw + 16 + 15) / 16;                       // row-buffer elements [0, 16 * groups) cover pixels up to tw + 12
   p.rb_pitch = 32 * p.groups + 32;                      // + slack for the dead columns' over-read
@@ -581,7 +581,7 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
     SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else
     SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  static const bool want_trace = getenv("SPK_STEM_TRACE") != nullptr;
+  static const bool want_trace = debug_env("SPK_STEM_TRACE") != nullptr;
   static long long* d_trace = nullptr;
   static int trace_left = 3;
   p.trace = nullptr;

@@ -446,7 +446,7 @@ int launch_stem_pool_t(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, co
   p.wp = wp;
   p.ldy = ldy;
   p.strips = (hp + kPoolRowsPerStrip - 1) / kPoolRowsPerStrip;
-  static const bool no_tma = getenv("SPK_STEM_NO_TMA") != nullptr;  // A/B switch: stage the strip with all threads
+  static const bool no_tma = debug_env("SPK_STEM_NO_TMA") != nullptr;  // A/B switch: stage the strip with all threads
   p.use_tma = (!no_tma && tw % 16 == 0 && tw <= 224 && ((uintptr_t)x & 15) == 0 && encode_fn() != nullptr) ? 1 : 0;
   p.groups = (tw + 16 + 15) / 16;                    // row-buffer elements [0, 16 * groups) cover pixels up to tw + 12
   p.rb_pitch = 32 * p.groups + 32;                   // + slack for the dead columns' over-read

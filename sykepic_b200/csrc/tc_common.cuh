@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "spk_debug.h"
+
 namespace spk {
 namespace tc {
 
@@ -207,7 +209,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  static const bool off = getenv("SPK_NO_PDL") != nullptr;
+  static const bool off = debug_env("SPK_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

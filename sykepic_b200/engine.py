@@ -123,6 +123,8 @@ class Engine:
         self.ctx = C.c_void_p()
         _lib.check(self.lib.spk_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(self.ctx)))
         self._keep = []  # numpy arrays referenced by the library during graph construction
+        self._channels = {}  # buffer id -> channels of the tensor it currently holds (graph construction)
+        self._slice_reads = False  # DenseNet: convolutions read the first c channels of a wider concat buffer
         self._build_graph()
         self.softmax_scale = float(np.float32(np.log(SOFTMAX_EXP)))  # probability.py:192-193
         # K1 decodes / resizes a whole chunk of a bin per launch (it only reaches HBM speed on thousands of ROIs);
@@ -157,6 +159,13 @@ class Engine:
     def _conv(self, sd, wkey, bnkey, inb, outb, stride, pad, relu, res=-1, in_off=0, out_off=0):
         w = _np(sd, wkey)
         cout, cin, kh, kw = w.shape
+        have = self._channels.get(inb)
+        if in_off == 0 and have is not None and inb != 0 and cin != have and not self._slice_reads:
+            # a grouped convolution (weight [Cout, Cin/groups, k, k]) would otherwise be run as a dense one over the
+            # first Cin/groups channels of its input
+            raise ValueError(f"{wkey}: weight expects {cin} input channels, the tensor it reads has {have} "
+                             "(grouped convolutions are not supported)")
+        self._channels[outb] = max(self._channels.get(outb, 0), out_off + cout) if out_off else cout
         bn = [None] * 4
         if bnkey is not None:
             bn = [_np(sd, f"{bnkey}.{n}") for n in ("weight", "bias", "running_mean", "running_var")]
@@ -172,8 +181,16 @@ class Engine:
         self._ck(self.lib.spk_net_bn_relu(self.ctx, inb, outb, channels, ptr(bn[0]), ptr(bn[1]), ptr(bn[2]), ptr(bn[3]),
                                           BN_EPS, int(relu)))
 
+    # torchvision architectures whose children()[:-1] this engine reproduces (TorchVisionNet, network.py:48-55).  Grouped
+    # or dilated variants (resnext*, wide_resnet* keeps plain convolutions and is fine) share the ResNet key layout but
+    # not its arithmetic, so the architecture NAME from config.ini is checked, not only the state_dict keys.
+    SUPPORTED_ARCH = re.compile(r"(resnet(18|34|50|101|152)|wide_resnet(50|101)_2|densenet(121|161|169|201))$")
+
     def _build_graph(self):
         sd = self.spec.state_dict
+        if not self.SUPPORTED_ARCH.match(str(self.spec.arch)):
+            raise ValueError(f"unsupported network {self.spec.arch!r}: this engine runs torchvision resnet18/34/50/101/152, "
+                             "wide_resnet50_2/101_2 and densenet121/161/169/201")
         self._ck(self.lib.spk_net_begin(self.ctx, self.th, self.tw, 1, self.precision, self.max_batch))
         if "base.0.conv0.weight" in sd:
             feat_buf = self._build_densenet(sd)
@@ -195,6 +212,13 @@ class Engine:
         self._ck(self.lib.spk_net_head(self.ctx, feat_buf, n, wp, bp, dm))
         self._ck(self.lib.spk_net_end(self.ctx))
         self._keep.clear()
+        slow = int(self.lib.spk_net_simt_layers(self.ctx))
+        if slow:
+            from .utils import logger
+
+            logger.get_logger("prob").warning(
+                f"{slow} convolution layer(s) of {self.spec.arch!r} have no tensor-core kernel in precision "
+                f"{self.precision_name!r} and run on CUDA cores (see stderr): expect a large slowdown")
 
     def _build_resnet(self, sd):
         """torchvision ResNet children()[:-1] (conv1, bn1, relu, maxpool, layer1-4, avgpool) from the
@@ -204,6 +228,7 @@ class Engine:
         self._conv(sd, "base.0.weight", "base.1", 0, a, 2, 3, True)
         x = ids.get()
         self._ck(self.lib.spk_net_maxpool(self.ctx, a, x, 3, 2, 1))
+        self._channels[x] = self._channels[a]
         ids.put(a)
         for stage in (4, 5, 6, 7):
             blocks = sorted({int(m.group(1)) for k in sd if (m := re.match(rf"base\.{stage}\.(\d+)\.", k))})
@@ -240,6 +265,7 @@ class Engine:
         this is the defined behaviour ("reference-undefined; parity vs torchvision")."""
         p = "base.0."
         ids = _IdPool()
+        self._slice_reads = True
         h = (self.th + 6 - 7) // 2 + 1
         w = (self.tw + 6 - 7) // 2 + 1
         a = ids.get()
@@ -514,6 +540,48 @@ def parse_adc(adc_text):
     _lib.check(lib.spk_adc_parse(data, len(data), cap, ptr(roi_id), ptr(w), ptr(h), ptr(start), C.byref(n), C.byref(lines)))
     k = n.value
     return roi_id[:k].copy(), w[:k].copy(), h[:k].copy(), start[:k].copy()
+
+
+def load_bin(sample_path, roi_buf, th, tw):
+    """One bin from disk through the C ABI (`spk_bin_load`: both file reads, the .adc parse and the geometry checks in one
+    call that holds no interpreter lock).  `roi_buf`: writable uint8 buffer (numpy array or pinned torch tensor) that
+    receives the .roi bytes.  -> (roi_id, w, h, start, roi_len).  Raises FaultyBin / EmptyResize / AdcParseError / OSError
+    as the per-bin error policy expects; `CapacityError` (with `.needed`) when `roi_buf` is too small."""
+    lib = _lib.load()
+    sample_path = Path(sample_path)
+    adc_path, roi_path = sample_path.with_suffix(".adc"), sample_path.with_suffix(".roi")
+    cap = os.path.getsize(adc_path) // 24 + 16  # a row has 24 comma-separated fields: at least 47 bytes with its newline
+    roi_id = np.empty(cap, np.int32)
+    w = np.empty(cap, np.int32)
+    h = np.empty(cap, np.int32)
+    start = np.empty(cap, np.int64)
+    n, roi_len = C.c_int64(), C.c_int64()
+    nbytes = roi_buf.numel() if hasattr(roi_buf, "numel") else roi_buf.size
+    rc = lib.spk_bin_load(os.fsencode(adc_path), os.fsencode(roi_path), ptr(roi_buf), nbytes, cap, ptr(roi_id), ptr(w), ptr(h),
+                          ptr(start), C.byref(n), C.byref(roi_len), th, tw)
+    if rc == _lib.SPK_ERR_CAPACITY and roi_len.value > nbytes:
+        raise CapacityError(roi_len.value)
+    _lib.check(rc)
+    k = n.value
+    return roi_id[:k], w[:k], h[:k], start[:k], roi_len.value
+
+
+class CapacityError(Exception):
+    def __init__(self, needed):
+        super().__init__(f"buffer too small: {needed} bytes needed")
+        self.needed = needed
+
+
+def write_prob_csv(csv_path, classes, roi_id, probs):
+    """`.prob.csv` formatted and written by the library in one call (probability.py:200-206) -> bytes written."""
+    lib = _lib.load()
+    header = ("roi," + ",".join(classes) + "\n").encode()
+    roi_id = np.ascontiguousarray(roi_id, dtype=np.int32)
+    probs = np.ascontiguousarray(probs, dtype=np.float32)
+    k = probs.shape[1] if probs.ndim == 2 else len(classes)
+    done = C.c_int64()
+    _lib.check(lib.spk_prob_csv_write(os.fsencode(csv_path), header, ptr(roi_id), ptr(probs), len(roi_id), k, C.byref(done)))
+    return done.value
 
 
 def validate_rois(w, h, start, roi_len, th, tw):

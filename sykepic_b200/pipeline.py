@@ -5,16 +5,18 @@ The reference handles one bin at a time on one thread (sykepic/compute/probabili
 host stages of a bin run on different threads so that the GPU never waits for the disk or for the
 text formatter:
 
-    loader thread(s)   .adc + .roi -> parsed descriptors (C ABI) + the byte stream in a pinned buffer
+    loader threads     .adc + .roi -> parsed descriptors + the byte stream in a pinned buffer, ONE C-ABI call per
+                       bin (`spk_bin_load`: file reads, parse, geometry checks) that holds no interpreter lock
     GPU thread         H2D, K1, K2 + K3 per batch, D2H into pinned buffers -- bin i+1 is submitted
                        before bin i's results are awaited, so the stream always has work queued
-    writer thread(s)   `%.5f` CSV text (C ABI) + file write
+    writer threads     `%.5f` CSV text + file write, one C-ABI call per bin (`spk_prob_csv_write`)
 
 Per-bin error policy is the reference's (probability.py:106-114): a bin that raises is logged
 ("Faulty raw data" for ValueError, "Unexpected error" otherwise) and skipped, the others go on.
 There is no collective and no cross-bin state: N of these pipelines (one per GPU) run side by side.
 """
 
+import os
 import queue
 import threading
 import time
@@ -59,8 +61,14 @@ class _PinnedPool:
 class BinPipeline:
     """Processes raw bins on one Engine.  `run(sample_paths)` -> set of processed sample names."""
 
-    def __init__(self, net, classes, out_dir, batch_size=None, force=False, suffix=".prob", loaders=2, writers=2, depth=3,
+    def __init__(self, net, classes, out_dir, batch_size=None, force=False, suffix=".prob", loaders=None, writers=None, depth=None,
                  want_labels=False):
+        # one B200 takes ~0.27 M ROI/s = 1.6 GB/s of .roi bytes; a loader thread copies 2.8-3.4 GB/s out of the page cache
+        # when it has a core to itself, a writer thread formats ~1 M ROI/s.  Four loaders keep the GPU fed with slack for
+        # cold files and busy hosts (SYKEPIC_LOADERS / SYKEPIC_WRITERS override).
+        loaders = loaders or int(os.environ.get("SYKEPIC_LOADERS", "4"))
+        writers = writers or int(os.environ.get("SYKEPIC_WRITERS", "2"))
+        depth = depth or 3
         self.net = net
         self.classes = list(classes)
         self.out_dir = out_dir
@@ -76,7 +84,7 @@ class BinPipeline:
 
     # ------------------------------------------------------------------ stages
     def _load(self, sample_path, pool):
-        """-> dict(sample, csv_path, roi_id, w, h, start, buf (pinned tensor), roi_len) or None (skipped)."""
+        """-> dict(sample, csv_path, roi_id, w, h, start, buf (pinned tensor), roi_len) or {"skip": True}."""
         sample_path = Path(sample_path)
         sample = sample_path.name
         csv_path = files.sample_csv_path(sample_path, self.out_dir, suffix=self.suffix)
@@ -87,24 +95,23 @@ class BinPipeline:
                 log.warning(f"{csv_path.name} already exists, skipping")
                 return {"sample": sample, "skip": True}
         t0 = time.perf_counter()
-        with open(sample_path.with_suffix(".adc"), "rb") as fh:
-            adc = fh.read()
-        roi_id, w, h, start = _engine.parse_adc(adc)
-        roi_path = sample_path.with_suffix(".roi")
-        n_bytes = roi_path.stat().st_size
+        n_bytes = sample_path.with_suffix(".roi").stat().st_size
         buf = pool.get(max(n_bytes, 16))
-        view = buf.numpy()
-        with open(roi_path, "rb") as fh:
-            got = fh.readinto(memoryview(view)[:n_bytes]) if n_bytes else 0
-        if got != n_bytes:
+        try:
+            try:
+                roi_id, w, h, start, roi_len = _engine.load_bin(sample_path, buf, self.net.th, self.net.tw)
+            except _engine.CapacityError as e:  # the file grew between stat and read
+                pool.put(buf)
+                buf = pool.get(e.needed)
+                roi_id, w, h, start, roi_len = _engine.load_bin(sample_path, buf, self.net.th, self.net.tw)
+        except BaseException:
             pool.put(buf)
-            raise ValueError(f"{roi_path.name}: short read")
-        _engine.validate_rois(w, h, start, n_bytes, self.net.th, self.net.tw)  # FaultyBin / EmptyResize are ValueErrors
+            raise
         with self._stat_lock:
             self.stats["load_s"] += time.perf_counter() - t0
-            self.stats["roi_bytes"] += n_bytes
+            self.stats["roi_bytes"] += roi_len
         return {"sample": sample, "csv_path": csv_path, "roi_id": roi_id, "w": w, "h": h, "start": start, "buf": buf,
-                "roi_len": n_bytes, "skip": False}
+                "roi_len": roi_len, "skip": False}
 
     def _write(self, item):
         t0 = time.perf_counter()
@@ -112,14 +119,12 @@ class BinPipeline:
         if len(roi_id) > 1 and np.any(np.diff(roi_id) < 0):  # results sorted by ROI id (probability.py:197)
             order = np.argsort(roi_id, kind="stable")
             roi_id, probs = roi_id[order], probs[order]
-        text = _engine.format_prob_csv(self.classes, roi_id, probs)
         csv_path = Path(item["csv_path"])
         csv_path.parent.mkdir(parents=True, exist_ok=True)
-        with open(csv_path, "wb") as fh:
-            fh.write(text)
+        n_text = _engine.write_prob_csv(csv_path, self.classes, roi_id, probs)
         with self._stat_lock:
             self.stats["write_s"] += time.perf_counter() - t0
-            self.stats["csv_bytes"] += len(text)
+            self.stats["csv_bytes"] += n_text
             self.stats["bins"] += 1
             self.stats["rois"] += len(roi_id)
 
@@ -130,21 +135,26 @@ class BinPipeline:
         sample_paths = list(sample_paths)
         processed = set()
         plock = threading.Lock()
-        todo = queue.Queue()
-        for i, sp in enumerate(sample_paths):
-            todo.put((i, sp))
+        todo = iter(enumerate(sample_paths))
+        todo_lock = threading.Lock()
+        stop = threading.Event()  # set when the driver loop leaves early: loaders stop taking work
         loaded = {}  # index -> item | exception marker, consumed in order so that bins finish in submission order
         loaded_cv = threading.Condition()
         slots = threading.Semaphore(self.depth + self.n_loaders)  # bounds the pinned memory in flight
         write_q = queue.Queue(maxsize=self.depth + 2)
 
         def loader():
-            while True:
-                try:
-                    i, sp = todo.get_nowait()
-                except queue.Empty:
+            while not stop.is_set():
+                # the slot is taken BEFORE the index: the lowest outstanding index always holds a slot, so the in-order
+                # consumer below can never be starved by later bins occupying every slot
+                if not slots.acquire(timeout=0.2):
+                    continue
+                with todo_lock:
+                    nxt = next(todo, None)
+                if nxt is None:
+                    slots.release()
                     return
-                slots.acquire()
+                i, sp = nxt
                 try:
                     item = self._load(sp, pool)
                 except ValueError:
@@ -237,6 +247,7 @@ class BinPipeline:
             if pending is not None:
                 finish(pending)
         finally:
+            stop.set()
             for _ in writers:
                 write_q.put(_STOP)
             for t in loaders + writers:

@@ -154,7 +154,8 @@ def _head(rng, sd, dims, logit_gain):
         sd[f"head.{i}.bias"] = (g * rng.uniform(-bound, bound, dims[i + 1])).astype(np.float32)
 
 
-def synth_state_dict(arch, n_classes=50, head=(256, 128), seed=0, randomize_bn=True, logit_gain=8.0, bn_stats=None):
+def synth_state_dict(arch, n_classes=50, head=(256, 128), seed=0, randomize_bn=True, logit_gain=8.0, bn_stats=None,
+                     res_gamma=1.0):
     """Seeded numpy state_dict with the key layout/shapes of `TorchVisionNet(arch, ...)`.
 
     `logit_gain` scales the last Linear so the softmax is peaky enough for the
@@ -163,6 +164,12 @@ def synth_state_dict(arch, n_classes=50, head=(256, 128), seed=0, randomize_bn=T
     npz under tests/golden/) overrides `*.running_mean` / `*.running_var` with
     statistics calibrated on synthetic ROIs, which makes the random network as
     input-sensitive as a trained one (tests/golden/make_golden.py).
+    `res_gamma` scales the affine parameters of the LAST BatchNorm of every
+    residual branch (ResNets): 1.0 leaves a branch as strong as the identity
+    path, which makes a deep random network amplify any perturbation (a 0.2 %
+    rounding becomes 13 % in ResNet-50's pooled features, tools/bf16_sweep.py);
+    trained ResNets' branches are small corrections of the identity path
+    (torchvision's zero_init_residual starts them at 0), which < 1 mimics.
     """
     rng = np.random.default_rng(10_000 + seed)
     sd = OrderedDict()
@@ -217,6 +224,11 @@ def synth_state_dict(arch, n_classes=50, head=(256, 128), seed=0, randomize_bn=T
     else:
         raise ValueError(f"unsupported network {arch!r}")
     _head(rng, sd, [feat, *head, n_classes], logit_gain)
+    if res_gamma != 1.0 and arch in RESNET_SPECS:
+        last = ".bn3." if RESNET_SPECS[arch][0] else ".bn2."
+        for k in sd:
+            if last in k and (k.endswith(".weight") or k.endswith(".bias")):
+                sd[k] = (sd[k] * np.float32(res_gamma)).astype(np.float32)
     if bn_stats is not None:
         for k in bn_stats:
             if k in sd:
@@ -247,7 +259,8 @@ max_rotation = 10
 
 
 def write_model_dir(model_dir, arch="resnet18", t=224, n_classes=50, head=(256, 128), seed=0, border="mode",
-                    imagenet_normalization=False, randomize_bn=True, classes=None, logit_gain=8.0, bn_stats=None):
+                    imagenet_normalization=False, randomize_bn=True, classes=None, logit_gain=8.0, bn_stats=None,
+                    res_gamma=1.0):
     """Writes config.ini + class_names.txt + best_state.pth (torch.save of a state_dict)."""
     import torch
 
@@ -259,6 +272,6 @@ def write_model_dir(model_dir, arch="resnet18", t=224, n_classes=50, head=(256, 
         CONFIG_TEMPLATE.format(network=arch, head=", ".join(str(h) for h in head), t=t,
                                norm="yes" if imagenet_normalization else "no", border=border)
     )
-    sd = synth_state_dict(arch, len(classes), head, seed, randomize_bn, logit_gain, bn_stats)
+    sd = synth_state_dict(arch, len(classes), head, seed, randomize_bn, logit_gain, bn_stats, res_gamma)
     torch.save(OrderedDict((k, torch.from_numpy(np.asarray(v))) for k, v in sd.items()), model_dir / "best_state.pth")
     return model_dir

@@ -15,14 +15,14 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def model_dirs(tmp_path_factory):
     """case name -> model dir identical to the one the goldens were generated with."""
-    from tests.cases import CASES, case_model_dir
+    from tests.cases import ALL_CASES, case_model_dir
 
     root = tmp_path_factory.mktemp("models")
     cache = {}
 
     def get(name):
         if name not in cache:
-            assert name in CASES
+            assert name in ALL_CASES
             cache[name] = case_model_dir(name, root)
         return cache[name]
 

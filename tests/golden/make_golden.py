@@ -1,6 +1,6 @@
 """Generate tests/golden/* by running the REFERENCE itself (build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]      (default: every case of tests/cases.py)
 
 Imports `/root/reference` read-only (sykepic.compute.probability /
 prediction / classification, sykepic.utils.ifcb, sykepic.train.*) with the shims
@@ -48,7 +48,7 @@ from sykepic.compute import classification, prediction, probability  # noqa: E40
 from sykepic.utils import ifcb as ref_ifcb  # noqa: E402
 
 from sykepic_b200 import synth  # noqa: E402
-from tests.cases import CASES, LOGIT_GAIN, case_bins  # noqa: E402
+from tests.cases import ALL_CASES, LOGIT_GAIN, case_bins  # noqa: E402
 
 torch.set_num_threads(8)
 
@@ -57,7 +57,28 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def calibrate_bn(name, arch, t, border, norm, classes, seed):
+def _reference_net(arch, n_classes):
+    """The reference's module for this architecture.  DenseNet: `TorchVisionNet` drops torchvision's functional
+    ReLU + pooling and raises at 224x224, so the defined behaviour -- torchvision's own forward with the
+    classifier replaced by the syke-pic head -- is built here from torchvision directly."""
+    from sykepic.train.network import TorchVisionNet
+
+    net = TorchVisionNet(arch, n_classes, None, [256, 128], [])
+    if arch.startswith("densenet"):
+        class TvForward(torch.nn.Module):
+            def __init__(self, inner):
+                super().__init__()
+                self.base, self.head = inner.base, inner.head
+
+            def forward(self, x):
+                f = torch.nn.functional.relu(self.base(x))
+                return self.head(torch.nn.functional.adaptive_avg_pool2d(f, 1).flatten(1))
+
+        return TvForward(net)
+    return net
+
+
+def calibrate_bn(name, arch, t, border, norm, classes, seed, gain=LOGIT_GAIN, res_gamma=1.0):
     """BatchNorm running statistics measured on synthetic ROIs (one train-mode pass, momentum 1).
 
     A random-init network with random running stats maps every ROI to nearly
@@ -66,10 +87,8 @@ def calibrate_bn(name, arch, t, border, norm, classes, seed):
     gates are exercised.  The result is committed (calib_<case>.npz) so the
     checkpoint is reproducible from the seed + this file anywhere.
     """
-    from sykepic.train.network import TorchVisionNet
-
-    sd = synth.synth_state_dict(arch, len(classes), (256, 128), seed, True, LOGIT_GAIN)
-    net = TorchVisionNet(arch, len(classes), None, [256, 128], [])
+    sd = synth.synth_state_dict(arch, len(classes), (256, 128), seed, True, gain, res_gamma=res_gamma)
+    net = _reference_net(arch, len(classes))
     net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
     for m in net.modules():
         if isinstance(m, torch.nn.BatchNorm2d):
@@ -94,23 +113,45 @@ def calibrate_bn(name, arch, t, border, norm, classes, seed):
     return stats
 
 
-def run_case(name, arch, t, border, norm, bins, classes, thresholds_files, tap_limit, seed):
-    print(f"== case {name}")
-    stats = calibrate_bn(name, arch, t, border, norm, classes, seed)
+def run_case(name, arch, t, border, norm, bins, classes, thresholds_files, tap_limit, seed, gain=LOGIT_GAIN, source="reference",
+             res_gamma=1.0):
+    """source "reference": everything below is produced by the reference's own code.  source "oracle" (DenseNet, which
+    the reference cannot run): decode / transform still come from the reference; network, CSV and labels from the oracle
+    restatement of torchvision's forward, cross-checked here against the torchvision module itself."""
+    print(f"== case {name} ({source})")
+    stats = calibrate_bn(name, arch, t, border, norm, classes, seed, gain, res_gamma)
     tmp = Path(tempfile.mkdtemp(prefix="golden_"))
     try:
         model_dir = synth.write_model_dir(tmp / "model", arch=arch, t=t, head=(256, 128), seed=seed, border=border,
-                                          imagenet_normalization=norm, classes=classes, logit_gain=LOGIT_GAIN,
-                                          bn_stats=stats)
+                                          imagenet_normalization=norm, classes=classes, logit_gain=gain,
+                                          bn_stats=stats, res_gamma=res_gamma)
         raw = tmp / "raw"
         sample_paths = []
         for bname, b in bins:
             sample_paths.append(synth.write_bin(raw, bname, b))
         out = tmp / "out"
-        processed = probability.main(sample_paths, model_dir, out, batch_size=16, num_workers=0, force=False,
-                                     progress_bar=False)
-        assert processed == {p.name for p in sample_paths}, processed
-        net, cls, img_shape, transform, device = probability.prepare_model(model_dir)
+        if source == "reference":
+            processed = probability.main(sample_paths, model_dir, out, batch_size=16, num_workers=0, force=False,
+                                         progress_bar=False)
+            assert processed == {p.name for p in sample_paths}, processed
+            net, cls, img_shape, transform, device = probability.prepare_model(model_dir)
+        else:
+            from oracle import pipeline as o_pipeline
+
+            from sykepic.train import config as ref_config
+            from configparser import ConfigParser
+
+            cfg = ConfigParser()
+            cfg.read(model_dir / "config.ini")
+            img_shape = ref_config.get_img_shape(cfg)
+            transform = ref_config.get_transforms(cfg, img_shape)[1]
+            net = _reference_net(arch, len(classes))
+            net.load_state_dict(torch.load(model_dir / "best_state.pth"), strict=True)
+            o_model = o_pipeline.prepare_model(model_dir)
+            for sp in sample_paths:
+                csv_path = ref_ifcb_csv_path(sp, out)
+                csv_path.parent.mkdir(parents=True, exist_ok=True)
+                csv_path.write_text(o_pipeline.process_bin(o_model, sp.with_suffix(".adc"), sp.with_suffix(".roi"), 16))
         net.eval()
         result = {}
         labels = {}
@@ -163,7 +204,14 @@ def run_case(name, arch, t, border, norm, bins, classes, thresholds_files, tap_l
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def ref_ifcb_csv_path(sample_path, out_dir):
+    from sykepic.utils import files as ref_files
+
+    return Path(ref_files.sample_csv_path(sample_path, out_dir, suffix=".prob"))
+
+
 def main():
+    wanted = sys.argv[1:] or list(ALL_CASES)
     fx = HERE / "ref_fixture"
     fx.mkdir(exist_ok=True)
     for rel in ("tests/data/raw/valid/D20180712T065600_IFCB114.adc", "tests/data/raw/valid/D20180712T065600_IFCB114.roi",
@@ -191,9 +239,10 @@ def main():
 
     classes = (fx / "class_names.txt").read_text().splitlines()
     thr = {"thresholds-2021": fx / "thresholds-2021.txt", "thresholds-zero": fx / "thresholds-zero.txt", "scalar-0.5": 0.5}
-    for name, c in CASES.items():
+    for name in wanted:
+        c = ALL_CASES[name]
         run_case(name, c["arch"], c["t"], c["border"], c["norm"], case_bins(name), classes, thr,
-                 tap_limit=c["tap_limit"], seed=c["seed"])
+                 tap_limit=c["tap_limit"], seed=c["seed"], gain=c.get("gain", LOGIT_GAIN), source=c.get("source", "reference"), res_gamma=c.get("res_gamma", 1.0))
 
 
 if __name__ == "__main__":

@@ -172,3 +172,49 @@ def test_adc_parse_agrees_with_python_int_on_random_fields():
         assert got == want, (text, got, want)
 
     check()
+
+
+def test_bin_load_reads_parses_and_validates(tmp_path):
+    """`spk_bin_load`: one call = both file reads + .adc parse + geometry checks; same descriptors as `spk_adc_parse`,
+    the .roi bytes land in the caller's buffer, and the reference's per-bin error cases map to the same exceptions."""
+    from sykepic_b200 import synth
+
+    b = synth.synth_bin(77, 60)
+    path = synth.write_bin(tmp_path, "D20210601T000000_IFCB114", b)
+    buf = np.full(len(b["roi_bytes"]) + 64, 0xAB, np.uint8)
+    rid, w, h, start, roi_len = engine.load_bin(path, buf, 224, 224)
+    want = engine.parse_adc(b["adc_text"])
+    for got, exp in zip((rid, w, h, start), want):
+        assert np.array_equal(got, exp)
+    assert roi_len == len(b["roi_bytes"]) and np.array_equal(buf[:roi_len], b["roi_bytes"]) and (buf[roi_len:] == 0xAB).all()
+    # buffer too small: the needed size is reported, nothing is written past the buffer
+    small = np.zeros(100, np.uint8)
+    with pytest.raises(engine.CapacityError) as ei:
+        engine.load_bin(path, small, 224, 224)
+    assert ei.value.needed == roi_len
+    # truncated .roi -> FaultyBin (a ValueError: "Faulty raw data", probability.py:111-112)
+    (tmp_path / "D20210601T000000_IFCB114.roi").write_bytes(b["roi_bytes"][:-3].tobytes())
+    with pytest.raises(_lib.FaultyBin):
+        engine.load_bin(path, buf, 224, 224)
+    # missing file -> OSError ("Unexpected error", :113-114); malformed .adc -> AdcParseError (a ValueError)
+    with pytest.raises(OSError):
+        engine.load_bin(tmp_path / "nope", buf, 224, 224)
+    bad = synth.write_bin(tmp_path, "D20210601T002000_IFCB114", {"adc_text": "1,2,3\n", "roi_bytes": np.zeros(4, np.uint8)})
+    with pytest.raises(_lib.AdcParseError):
+        engine.load_bin(bad, buf, 224, 224)
+    # empty bin: no ROIs, no bytes
+    empty = synth.write_bin(tmp_path, "D20210601T004000_IFCB114", {"adc_text": "", "roi_bytes": np.zeros(0, np.uint8)})
+    rid, w, h, start, roi_len = engine.load_bin(empty, buf, 224, 224)
+    assert len(rid) == 0 and roi_len == 0
+
+
+def test_prob_csv_write_equals_format(tmp_path):
+    rng = np.random.default_rng(3)
+    classes = [f"c{i}" for i in range(50)]
+    probs = rng.random((321, 50), dtype=np.float32)
+    rid = np.arange(1, 322, dtype=np.int32)
+    n = engine.write_prob_csv(tmp_path / "x.prob.csv", classes, rid, probs)
+    data = (tmp_path / "x.prob.csv").read_bytes()
+    assert n == len(data) and data == engine.format_prob_csv(classes, rid, probs)
+    with pytest.raises(OSError):
+        engine.write_prob_csv(tmp_path / "no_such_dir" / "x.csv", classes, rid, probs)
