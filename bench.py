@@ -19,6 +19,7 @@ port timed on this box's host cores on a bounded sample.
 import argparse
 import json
 import os
+import shutil
 import sys
 import tempfile
 import threading
@@ -54,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-detail", metavar="FILE", help="write the per-launch timing table of the roofline pass")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--e2e-bins", type=int, default=64, help="IFCB bins per GPU of the end-to-end (files -> CSV) leg")
+    ap.add_argument("--profile-events", metavar="FILE", help="also write the per-launch CUDA-event table (serialised launches)")
     return ap.parse_args()
 
 
@@ -411,41 +414,56 @@ def run_b200(args):
     last_probs = probs[last_lo:last_lo + args.batch].cpu().numpy()
     last_label = label[last_lo:last_lo + args.batch].cpu().numpy()
 
-    # ---- e2e: host API on whole chunks (a bin is what the API takes), pinned host buffers, H2D + D2H inside the timed region
-    host_in = [(w, h, start, torch.from_numpy(roi).pin_memory().numpy()) for w, h, start, roi in chunks]
-    ids = np.arange(chunk, dtype=np.int32)
+    # ---- e2e: the PRODUCT path.  `probability.main` over IFCB bins on local disk (tmpfs): .adc/.roi files -> loader threads
+    # (spk_bin_load into pinned buffers) -> H2D -> K1/K2/K3 -> D2H -> writer threads (%.5f CSV files), first file open to last
+    # CSV closed, with the engine built before the clock (a service builds it once; the reference rebuilds its model per call).
+    from sykepic_b200 import pipeline, shard, synth
+    from sykepic_b200.compute import probability
 
-    def submit_host(i):
-        w, h, start, roi = host_in[i % n_pool]
-        return eng.submit_rois(w, h, start, roi, want_labels=True)
-
-    # warm-up: two bins in flight, so that both sets of pinned staging buffers exist before the clock starts
-    h0, h1 = submit_host(0), submit_host(1)
-    h0.result()
-    h1.result()
-    for i in range(2):  # ... and two more at steady state (host threads and clocks up on every rank)
-        submit_host(i).result()
+    shard.pin_to_gpu_node(local)
+    base = "/dev/shm" if Path("/dev/shm").is_dir() else None
+    froot = Path(tempfile.mkdtemp(prefix=f"spk_bench_files_r{rank}_", dir=base))
+    raw, out_dir = froot / "raw", froot / "out"
+    raw.mkdir()
+    n_files = max(8, args.e2e_bins)
+    distinct = [synth.synth_bin(3000 + 10 * rank + i) for i in range(min(4, n_files))]  # ~5000 ROIs each, IFCB geometry
+    free = shutil.disk_usage(froot).free
+    per_bin = max(len(d["roi_bytes"]) for d in distinct) * 1.15
+    n_files = int(max(8, min(n_files, 0.5 * free / world / per_bin)))
+    files_rois = files_bytes = 0
+    for i in range(n_files):
+        d = distinct[i % len(distinct)]
+        name = synth.bin_name(72 * rank + i)
+        if i < len(distinct):
+            synth.write_bin(raw, name, d)
+        else:  # same content under another name: a different file to open, read and answer
+            first = synth.bin_name(72 * rank + i % len(distinct))
+            shutil.copyfile(raw / f"{first}.adc", raw / f"{name}.adc")
+            shutil.copyfile(raw / f"{first}.roi", raw / f"{name}.roi")
+        files_rois += int((d["w"] > 0).sum())
+        files_bytes += len(d["roi_bytes"])
+    paths = sorted(q.with_suffix("") for q in raw.glob("*.roi"))
+    warm = probability.main(paths[:4], mdir, froot / "warm", batch_size=args.batch, force=True, progress_bar=False,
+                            precision=args.precision, engine=eng)
+    assert len(warm) == 4
     barrier()
-    e2e_calls = max(24, -(-args.steps // G))  # >= 0.4 s per rank: eight calls were at the mercy of one slow host thread
     t0 = time.perf_counter()
-    # the host API as `probability.main` drives it (pipeline.BinPipeline): bin i+1 is submitted before bin i is awaited
-    pending = None
-    for i in range(e2e_calls):
-        nxt = submit_host(i)
-        if pending is not None:
-            pending.result()
-        pending = nxt
-    pending.result()
+    done = probability.main(paths, mdir, out_dir, batch_size=args.batch, force=True, progress_bar=False, precision=args.precision,
+                            engine=eng)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert len(done) == len(paths), (len(done), len(paths))
+    stage = dict(pipeline.LAST_STATS[-1])
+    n_csv = len(list(out_dir.rglob("*.prob.csv")))
+    assert n_csv == len(paths)
     barrier()
-    e2e_steps = e2e_calls * G
-    h2d = (int(np.mean(in_bytes)) + chunk * 16) // G
-    d2h = args.batch * (K * 4 + 4 + 1)
+    h2d = int(files_bytes / files_rois * args.batch) + 16 * args.batch
+    d2h = args.batch * K * 4
+    shutil.rmtree(froot, ignore_errors=True)
 
-    # ---- roofline pass: per-launch CUDA events on the engine's stream (separate pass, same inputs)
+    # ---- roofline pass: IN-STEP time of every launch from in-kernel global-timer stamps (launches stay back to back, PDL on)
     prof_steps = G  # one full chunk cycle: K1 once, K2 + K3 G times
-    eng.profile_begin()
+    eng.profile_begin(stamps=True)
     with torch.cuda.stream(stream):
         for i in range(prof_steps):
             flush.zero_()
@@ -456,20 +474,56 @@ def run_b200(args):
     if args.profile_detail and rank == 0:
         agg = {}
         for cat, ms, fl, by, what in detail:
+            what, _, span = what.partition(" |span_ms=")
+            a = agg.setdefault((cat, what), [0, 0.0, fl, by, 0.0])
+            a[0] += 1
+            a[1] += ms
+            a[4] += float(span or 0.0)
+        with open(args.profile_detail, "w") as fh:
+            fh.write("category\tlaunches\tin_step_ms\tTFLOP/s\tGB/s(algorithmic)\tspan_ms(first CTA start -> last CTA end)\twhat\n")
+            for (cat, what), (cnt, ms, fl, by, span) in agg.items():
+                avg = max(ms / cnt, 1e-9)
+                fh.write(f"{cat}\t{cnt}\t{avg:.4f}\t{fl / avg / 1e9:.1f}\t{by / avg / 1e6:.1f}\t{span / cnt:.4f}\t{what}\n")
+    if args.profile_events and rank == 0:  # the old per-launch CUDA-event table (serialises the launches; for comparison)
+        eng.profile_begin(stamps=False)
+        with torch.cuda.stream(stream):
+            for i in range(prof_steps):
+                flush.zero_()
+                step_device(i)
+        ev = eng.profile_read(detail=True)
+        eng.profile_end()
+        agg = {}
+        for cat, ms, fl, by, what in ev.pop("detail"):
             a = agg.setdefault((cat, what), [0, 0.0, fl, by])
             a[0] += 1
             a[1] += ms
-        with open(args.profile_detail, "w") as fh:
+        with open(args.profile_events, "w") as fh:
             fh.write("category\tlaunches\tavg_ms\tTFLOP/s\tGB/s(algorithmic)\twhat\n")
             for (cat, what), (cnt, ms, fl, by) in agg.items():
-                avg = ms / cnt
-                fh.write(f"{cat}\t{cnt}\t{avg:.4f}\t{fl / avg / 1e9:.1f}\t{by / avg / 1e6:.1f}\t{what}\n")
+                fh.write(f"{cat}\t{cnt}\t{ms / cnt:.4f}\t{fl / (ms / cnt) / 1e9:.1f}\t{by / (ms / cnt) / 1e6:.1f}\t{what}\n")
 
-    # ---- reduce over ranks: max time
-    t = torch.tensor([ms_total, e2e_s, wall], dtype=torch.float64, device=dev)
+    # ---- K1 alone (a kernel timed in isolation: CUDA events on its stream, L2 flushed before each launch)
+    k1_ms = []
+    with torch.cuda.stream(stream):
+        for r in range(6):
+            roi_d, start_d, w_d, h_d, roi_len = dev_in[r % n_pool]
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            eng.preprocess(roi_d, roi_len, start_d, w_d, h_d, chunk, eng._x)
+            e1.record(stream)
+            k1_ms.append((e0, e1, in_bytes[r % n_pool]))
+    stream.synchronize()
+    k1 = sorted((a.elapsed_time(b), nb) for a, b, nb in k1_ms[1:])[len(k1_ms[1:]) // 2]
+
+    # ---- reduce over ranks: max time, summed ROIs
+    t = torch.tensor([ms_total, e2e_s, wall, -float(files_rois)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(files_rois), float(len(paths))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, wall = t.tolist()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total, e2e_s, wall, _ = t.tolist()
+    all_rois, all_bins = tot.tolist()
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -477,22 +531,31 @@ def run_b200(args):
         total_prof_ms = sum(step_ms.values())
         tc = prof.get("conv_tc")
         mean_in = float(np.mean(in_bytes))
+        burst, sustained = float(pk["bf16_tflops"]), float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
+        # which regime did THIS run see?  The sustained figure belongs to seconds of tensor load under the power cap
+        # (MEASURED_PEAKS: 1312 MHz); a run whose SM clock stayed near the maximum is held to the burst figure.
+        sm, sm_max = clocks.get("sm_mhz"), clocks.get("sm_max_mhz")
+        regime = "sustained" if (sm and sm_max and sm < 0.8 * sm_max) else "burst"
+        peak = sustained if regime == "sustained" else burst
+        traffic_file = ROOT / "profiles" / "r2_traffic.json"
+        traffic = json.loads(traffic_file.read_text()) if traffic_file.exists() else {}
         if tc:
             ach = tc["flops"] / (tc["ms"] * 1e-3) / 1e12
-            peak = float(pk["bf16_tflops_sustained"] if "bf16_tflops_sustained" in pk else pk["bf16_tflops"])
             roofline = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions, all launches of a step (conv3x3_hp / conv_pair / conv_tc kernels)",
                         "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "peak_kind": f"{pk_kind} bf16 sustained (cuBLAS)", "traffic": None,
-                        "launches_per_step": tc["launches"] // prof_steps, "share_of_step": step_ms["conv_tc"] / total_prof_ms}
-            # the dominant single kernel of the step (largest share): its own achieved rate and, from the committed ncu
-            # capture of the same workload, its DRAM traffic per launch
+                        "peak_kind": f"{pk_kind} bf16 {regime} (cuBLAS); SM clock median {sm} of {sm_max} MHz during the timed region",
+                        "frac_of_burst": ach / burst, "frac_of_sustained": ach / sustained, "traffic": None,
+                        "launches_per_step": tc["launches"] // prof_steps, "share_of_step": step_ms["conv_tc"] / total_prof_ms,
+                        "timing": "in-step time per launch from in-kernel global-timer stamps (end - max(previous end, own start)); "
+                                  "launches back to back with programmatic dependent launch, as in the timed region",
+                        "in_step_ms_sum": total_prof_ms}
             dom = [(ms, fl) for cat, ms, fl, by, what in detail if "[halo pair]" in what and "64->64" in what]
-            tr_file = ROOT / "profiles" / "r1b_traffic.json"
-            if dom and args.arch == "resnet18" and args.batch == 256:
+            if dom and args.arch == "resnet18":
                 d_ms, d_fl = sum(m for m, _ in dom), sum(f for _, f in dom)
-                tr = json.loads(tr_file.read_text()).get("conv3x3_hp_kernel<64>") if tr_file.exists() else None
+                tr = traffic.get("conv3x3_hp_kernel<64>")
                 roofline["dominant"] = {"kernel": "conv3x3_hp_kernel<64> (3x3 64->64 @56x56, 4 launches per step)",
                                         "achieved": d_fl / (d_ms * 1e-3) / 1e12, "frac": d_fl / (d_ms * 1e-3) / 1e12 / peak,
+                                        "frac_of_burst": d_fl / (d_ms * 1e-3) / 1e12 / burst,
                                         "ms_per_launch": d_ms / len(dom), "share_of_step": d_ms / prof_steps / total_prof_ms,
                                         "traffic": tr["dram_bytes_per_launch"] if tr else None,
                                         "algorithmic_bytes": tr["algorithmic_bytes_per_launch"] if tr else None,
@@ -501,17 +564,8 @@ def run_b200(args):
         else:
             cs = prof.get("conv_simt", {"flops": 0.0, "ms": 1.0, "launches": 0})
             ach = cs["flops"] / (cs["ms"] * 1e-3) / 1e12
-            peak = float(pk["bf16_tflops"])
             roofline = {"bound": "tensor", "kernel": "conv_simt_kernel (CUDA-core FFMA; no tensor-core path in this precision)",
-                        "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_kind": pk_kind, "traffic": None}
-        pre = prof.get("preprocess")
-        pre_roof = None
-        if pre:
-            pre_bytes = pre["bytes"] + mean_in * pre["launches"]
-            g = pre_bytes / (pre["ms"] * 1e-3) / 1e9
-            pre_roof = {"bound": "hbm", "kernel": "preprocess_kernel", "achieved": g, "peak": float(pk["hbm_gbs"]), "unit": "GB/s",
-                        "frac": g / float(pk["hbm_gbs"]), "bytes_per_roi": pre_bytes / (pre["launches"] * chunk),
-                        "rois_per_launch": chunk, "ms_per_launch": pre["ms"] / pre["launches"]}
+                        "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "peak_kind": pk_kind, "traffic": None}
         value = args.gpus * args.batch * args.steps / (ms_total * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -524,16 +578,30 @@ def run_b200(args):
                        "l2": "flushed between steps (256 MiB memset outside the timed events)",
                        "mean_roi_bytes": mean_in / chunk,
                        "k1_chunk": f"K1 decodes {chunk} ROIs ({G} batches) per launch, every {G}th step; K2+K3 per batch",
+                       "checkpoint": f"tests/cases.py {BENCH_CASE.get(args.arch, 'seeded random init')}",
                        "conv_gflop_per_roi_logical": CONV_GFLOP.get(args.arch) if args.target == 224 else None},
-            "e2e": {"value": args.gpus * args.batch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": f"Engine.submit_rois(...).result() on bins of {chunk} ROIs, one bin in flight ahead (as probability.main / BinPipeline does): pinned host in, host numpy out, {e2e_calls} calls"},
+            "e2e": {"value": all_rois / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": f"probability.main(paths, model_dir, out, batch_size={args.batch}, engine=<prebuilt>) per GPU process: "
+                           f"{int(all_bins)} IFCB bins ({int(all_rois)} ROIs) as .adc/.roi files on {base or 'tmp'} -> .prob.csv files; "
+                           "first file open to last CSV closed, max over ranks",
+                    "bins": int(all_bins), "rois": int(all_rois), "seconds": e2e_s,
+                    "stage_seconds_rank0": {k: round(float(stage.get(k, 0.0)), 4) for k in ("load_s", "gpu_wait_s", "write_s", "run_s")},
+                    "host_threads_rank0": {"loaders": int(os.environ.get("SYKEPIC_LOADERS", "4")), "writers": int(os.environ.get("SYKEPIC_WRITERS", "2"))}},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
             "roofline": roofline,
-            "roofline_preprocess": pre_roof,
+            "roofline_preprocess": None,
             "kernel_ms_per_step": step_ms,
             "wall_s_timed_region": wall,
         }
+        k1_bytes = k1[1] + chunk * (16 + args.target * args.target)  # ROI bytes read + descriptors + the u8 planes written
+        k1_gbs = k1_bytes / (k1[0] * 1e-3) / 1e9
+        pre_tr = traffic.get("preprocess_u8_kernel") or {}
+        line["roofline_preprocess"] = {"bound": "hbm", "kernel": "preprocess_u8_kernel (+ classify / heavy-tail cluster kernel)", "achieved": k1_gbs,
+                                       "peak": float(pk["hbm_gbs"]), "unit": "GB/s", "frac": k1_gbs / float(pk["hbm_gbs"]),
+                                       "bytes_per_roi": k1_bytes / chunk, "rois_per_launch": chunk, "ms_per_launch": k1[0],
+                                       "traffic": pre_tr.get("dram_bytes_per_launch"), "traffic_source": pre_tr.get("source"),
+                                       "timing": "CUDA events around one spk_preprocess call, L2 flushed, median of 5"}
         line["parity"] = parity_check(args, mdir, chunks[last_chunk], last_lo, last_probs, last_label)
         if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only (under torchrun OMP_NUM_THREADS is 1)
             rate, n_done, cores = cpu_port_rate(args, mdir, chunks, args.cpu_seconds)

@@ -82,6 +82,15 @@ int64_t spk_launch_count(const spk_ctx* ctx);
  * costs nothing then. */
 enum { SPK_PROF_PREPROCESS = 0, SPK_PROF_CONV_TC = 1, SPK_PROF_CONV_SIMT = 2, SPK_PROF_STEM = 3,
        SPK_PROF_POOL = 4, SPK_PROF_BN_RELU = 5, SPK_PROF_HEAD = 6, SPK_PROF_CATEGORIES = 8 };
+/* SPK_PROFILE_EVENTS (default): CUDA events around every launch -- simple, but an event between two launches serialises
+ * them (no programmatic-dependent-launch overlap) and adds a few microseconds each, so the per-kernel times sum to MORE
+ * than the step.  SPK_PROFILE_STAMPS: every tcgen05 kernel, the stem and the head stamp their earliest CTA start / latest
+ * CTA end on the GPU's global timer into a context-owned buffer; the launches stay back to back as in production.
+ * spk_profile_read then reports per launch the IN-STEP time = end - max(previous launch's end, own start), which sums to
+ * the step, and in the detail line the raw span (" |span_ms=..."); kernels without stamps (pools, CUDA-core convolutions,
+ * K1) are folded into the next stamped launch. */
+enum { SPK_PROFILE_EVENTS = 0, SPK_PROFILE_STAMPS = 1 };
+int spk_profile_mode(spk_ctx* ctx, int mode);
 int spk_profile_begin(spk_ctx* ctx);
 int spk_profile_read(spk_ctx* ctx, double ms[SPK_PROF_CATEGORIES], double flops[SPK_PROF_CATEGORIES],
                      double bytes[SPK_PROF_CATEGORIES], int64_t launches[SPK_PROF_CATEGORIES],

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "spk_synchronize": (_i, [_p]),
     "spk_last_error": (C.c_char_p, [_p]),
     "spk_launch_count": (_i64, [_p]),
+    "spk_profile_mode": (_i, [_p, _i]),
     "spk_profile_begin": (_i, [_p]),
     "spk_profile_read": (_i, [_p, _p, _p, _p, _p, _p, _i64]),
     "spk_profile_end": (_i, [_p]),

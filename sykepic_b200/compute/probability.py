@@ -107,18 +107,23 @@ def main(
     *,
     precision=None,
     devices=None,
+    engine=None,
 ):
-    """`num_workers` is accepted for compatibility; there are no loader processes here."""
-    devices = _devices(devices)
+    """`num_workers` is accepted for compatibility; there are no loader processes here.
+    `engine`: an already built `Engine` for `model_dir` on the (single) device -- callers that process several batches
+    of bins with one model (services, bench.py) skip the per-call model construction the reference pays (:77)."""
+    devices = [engine.device.index] if engine is not None else _devices(devices)
     precision = precision or DEFAULT_PRECISION
-    spec = _engine.ModelSpec.from_dir(model_dir)
+    spec = engine.spec if engine is not None else _engine.ModelSpec.from_dir(model_dir)
     # `batch_size` is the reference's DataLoader batch (CLI default 64).  Results do not depend on how ROIs are batched
     # (tests/test_gpu_network.py::test_batch_split_and_partial_batches), and the GPU wants large launches: ResNet-18 runs
     # at 263 k ROI/s with 256 ROIs per launch sequence, 280 k with 512, 284 k with 1024 -- so smaller requests are raised.
     max_batch = max(int(batch_size), int(os.environ.get("SYKEPIC_MIN_BATCH", "1024")), 1)
+    if engine is not None:
+        max_batch = engine.max_batch
 
     def make_params(dev):
-        net = _engine.Engine(spec, device=dev, precision=precision, max_batch=max_batch)
+        net = engine if engine is not None else _engine.Engine(spec, device=dev, precision=precision, max_batch=max_batch)
         return net, EvalParams(batch_size=max_batch, num_workers=num_workers, classes=spec.classes,
                                img_shape=spec.img_shape, transform=None, device=net.device)
 
@@ -139,7 +144,8 @@ def main(
                     cur, nxt = nxt, ahead(i + 1)
                     process_images(img_paths, net, params, csv_of(sample), force, decoded=cur.result() if cur else None)
         finally:
-            net.close()
+            if engine is None:
+                net.close()
         return None
 
     sample_paths = list(sample_paths)
@@ -155,7 +161,8 @@ def main(
             pipe = pipeline.BinPipeline(net, params.classes, out_dir, batch_size=params.batch_size, force=force, suffix=FILE_SUFFIX)
             return pipe.run(paths, progress=bar)
         finally:
-            net.close()
+            if engine is None:
+                net.close()
 
     try:
         if len(devices) <= 1:
@@ -246,6 +253,7 @@ def _shard_process(dev, paths, model_dir, out_dir, batch_size, num_workers, forc
     try:
         from .. import pipeline
 
+        shard.pin_to_gpu_node(dev)  # this process serves one GPU: keep its host threads on that GPU's NUMA node
         done = main([Path(p) for p in paths], model_dir, out_dir, batch_size, num_workers, force, progress_bar=False,
                     precision=precision, devices=[dev])
         queue.put((dev, sorted(done), None, pipeline.LAST_STATS[-1] if pipeline.LAST_STATS else None))

@@ -55,6 +55,8 @@ struct alignas(64) HpParams {
   int na;           // A ring depth
   int reverse;      // walk the units from the last image to the first: the tensors the previous kernel touched last
                     // are still in L2 (consecutive layers alternate direction)
+  unsigned long long* stamp;  // profiling (stamp mode): global-timer slot of this launch, else nullptr
+  int dbg;          // debug build only (SPK_HP_DBG): 1 = skip the global stores, 2 = skip the residual loads
   long long* trace; // debug (SPK_HP_TRACE=1): clock64 stamps of the leader MMA issuer of cluster 3, else nullptr
 };
 
@@ -108,6 +110,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   pdl_trigger();
+  stamp_begin(p.stamp);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(a_full(s), 1);
@@ -253,7 +256,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
     auto res_load = [&](int u, U8 (&r)[kSlabs][2]) {
       int img, h0;
       const bool tile_ok = tile_coords(u, img, h0);
-      if (works && tile_ok && (jc < p.w) && (jr < p.hb) && (h0 + jr < p.h)) {
+      if (works && tile_ok && (jc < p.w) && (jr < p.hb) && (h0 + jr < p.h) && !(p.dbg & 2)) {
         const __nv_bfloat16* rp = p.res + (((long long)img * p.h + (h0 + jr)) * p.w + jc) * p.ldres + half * 32;
 #pragma unroll
         for (int slab = 0; slab < kSlabs; ++slab)
@@ -325,7 +328,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
                 o.v[c4 * 4 + t] = *reinterpret_cast<const uint32_t*>(&b2);
               }
             }
-            stg_v8(yp + c8 * 16, o);
+            if (!(p.dbg & 1)) stg_v8(yp + c8 * 16, o);
           }
         }
       }
@@ -338,6 +341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv3x3
 
   tc_fence_before();
   cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still read this CTA's shared memory
+  stamp_end(p.stamp);
   if (warp == 1) {
     tc_fence_after();
     tmem2_dealloc(tmem_base, kTmemAlloc);
@@ -489,6 +493,9 @@ int hp_conv_launch(spk_ctx* ctx, HpConvPlan* p, int n, const void* x, const void
   prm.m_tiles = n * prm.tiles_h;
   prm.units = (prm.m_tiles + 1) / 2;
   const int clusters = std::min(prm.units, ctx->sm_count / 2);
+  static const int dbg = debug_env("SPK_HP_DBG") ? atoi(debug_env("SPK_HP_DBG")) : 0;
+  prm.dbg = dbg;
+  prm.stamp = ctx->cur_stamp;
   static const bool want_trace = debug_env("SPK_HP_TRACE") != nullptr;
   static long long* d_trace = nullptr;
   static int trace_left = 6;

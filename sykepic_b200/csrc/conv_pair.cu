@@ -59,6 +59,7 @@ struct alignas(64) PairParams {
   int taps, kchunks, cin_pad;
   int stages, res_slots;
   int reverse;  // walk the units last-to-first (consecutive layers alternate direction: the previous kernel's last tiles are in L2)
+  unsigned long long* stamp;  // profiling (stamp mode): global-timer slot of this launch, else nullptr
   long long* trace;  // debug (SPK_PAIR_TRACE=1): clock64 stamps of one CTA's epilogue thread 0
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
@@ -99,6 +100,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   pdl_trigger();
+  stamp_begin(p.stamp);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(full_bar(s), 1);   // used in the leader only: its producer's arrive.expect_tx
@@ -346,6 +348,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
 
   tc_fence_before();
   cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still read this CTA's shared memory
+  stamp_end(p.stamp);
   if (warp == 1) {
     tc_fence_after();
     tmem2_dealloc(tmem_base, kTmemCols);
@@ -589,6 +592,7 @@ int pair_conv_launch(spk_ctx* ctx, PairConvPlan* p, int n, const void* x, const 
   prm.m_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img;
   prm.units = ((prm.m_tiles + 1) / 2) * prm.tiles_n;
   const int clusters = std::min(prm.units, ctx->sm_count / 2);
+  prm.stamp = ctx->cur_stamp;
   static const bool want_trace = debug_env("SPK_PAIR_TRACE") != nullptr;
   static long long* d_trace = nullptr;
   static int trace_left = 4;

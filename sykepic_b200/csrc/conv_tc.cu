@@ -60,6 +60,7 @@ struct alignas(64) TcParams {
   const float* pre_scale;
   const float* pre_shift;
   int pre_c, pre_relu;
+  unsigned long long* stamp;  // profiling (stamp mode): global-timer slot of this launch, else nullptr
   signed char tap_map[kMaxTaps + 3], tap_dh[kMaxTaps + 3], tap_dw[kMaxTaps + 3];
 };
 
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   tc::pdl_trigger();
+  tc::stamp_begin(p.stamp);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -533,6 +535,7 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
 
   tc_fence_before();
   __syncthreads();
+  tc::stamp_end(p.stamp);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols) : "memory");
@@ -868,6 +871,7 @@ int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void
   prm.res = (const __nv_bfloat16*)res;
   prm.y = (__nv_bfloat16*)y;
   prm.y2 = (__nv_bfloat16*)y_ds;
+  prm.stamp = ctx->cur_stamp;
   if (p->ds && !y_ds) return fail(ctx, SPK_ERR_INVALID, "tcgen05 convolution: fused downsample without an output");
   prm.tiles_img = (n + prm.nb - 1) / prm.nb;
   prm.total_tiles = prm.tiles_w * prm.tiles_h * prm.tiles_img * prm.tiles_n;

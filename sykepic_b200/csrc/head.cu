@@ -46,7 +46,7 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS) head_kernel(const T* act, int hw, int F, const float* __restrict__ W,
                                                        const float* __restrict__ bias, int K, float scale,
                                                        const int32_t* __restrict__ thr_q, float* logits, float* probs,
-                                                       int32_t* label, uint8_t* classified) {
+                                                       int32_t* label, uint8_t* classified, unsigned long long* stamp) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* feat = reinterpret_cast<float*>(smem);
   float* logit = feat + F;
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(THREADS) head_kernel(const T* act, int hw, int
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n = blockIdx.x;
   tc::pdl_trigger();
+  tc::stamp_begin(stamp);
   tc::pdl_wait();  // the activations are the previous kernel's output
 
   // global average pool: sum over the hw positions in position order, then divide (fp32)
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(THREADS) head_kernel(const T* act, int hw, int
     label[n] = best_thr >= 0 ? best_thr : best;
     if (classified) classified[n] = best_thr >= 0 ? 1 : 0;
   }
+  tc::stamp_end(stamp);  // (thread 0 is the last one working)
 }
 
 }  // namespace
@@ -180,17 +182,17 @@ int launch_head(spk_ctx* ctx, const void* act, int act_dtype, int64_t n, int hw,
     if (smem > 48 * 1024)
       SPK_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPK_CUDA_OK(ctx, tc::launch_pdl(head_kernel<float>, dim3((unsigned)n), dim3(THREADS), smem, ctx->stream, (const float*)act, hw, feat, w_kf,
-                                    bias, k, softmax_scale, thr_q, logits, probs, label, classified));
+                                    bias, k, softmax_scale, thr_q, logits, probs, label, classified, ctx->cur_stamp));
   } else if (act_dtype == SPK_DTYPE_BF16) {
     if (smem > 48 * 1024)
       SPK_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPK_CUDA_OK(ctx, tc::launch_pdl(head_kernel<__nv_bfloat16>, dim3((unsigned)n), dim3(THREADS), smem, ctx->stream,
-                                    (const __nv_bfloat16*)act, hw, feat, w_kf, bias, k, softmax_scale, thr_q, logits, probs, label, classified));
+                                    (const __nv_bfloat16*)act, hw, feat, w_kf, bias, k, softmax_scale, thr_q, logits, probs, label, classified, ctx->cur_stamp));
   } else if (act_dtype == SPK_DTYPE_SPLIT) {
     if (smem > 48 * 1024)
       SPK_CUDA_OK(ctx, cudaFuncSetAttribute(head_kernel<SplitF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SPK_CUDA_OK(ctx, tc::launch_pdl(head_kernel<SplitF>, dim3((unsigned)n), dim3(THREADS), smem, ctx->stream, (const SplitF*)act, hw, feat, w_kf,
-                                    bias, k, softmax_scale, thr_q, logits, probs, label, classified));
+                                    bias, k, softmax_scale, thr_q, logits, probs, label, classified, ctx->cur_stamp));
   } else {
     return fail(ctx, SPK_ERR_UNSUPPORTED, "head: dtype %d", act_dtype);
   }

@@ -16,6 +16,8 @@
 
 namespace spk {
 
+constexpr int kStampCapHost = 8192;  // == tc::kStampCap (tc_common.cuh)
+
 std::string& tls_error() {
   static thread_local std::string e;
   return e;
@@ -46,6 +48,16 @@ ProfScope::ProfScope(spk_ctx* c, int category, double flops, double bytes, const
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   r.what = buf;
+  r.slot = -1;
+  r.start = r.stop = nullptr;
+  if (c->prof_mode == SPK_PROFILE_STAMPS) {
+    if (!c->d_stamps || (int)c->prof.size() >= kStampCapHost) return;
+    r.slot = (int)c->prof.size();
+    c->cur_stamp = c->d_stamps + r.slot;
+    idx = r.slot;
+    c->prof.push_back(r);
+    return;
+  }
   if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
   cudaEventRecord(r.start, c->stream);
   idx = (int)c->prof.size();
@@ -53,7 +65,11 @@ ProfScope::ProfScope(spk_ctx* c, int category, double flops, double bytes, const
 }
 
 ProfScope::~ProfScope() {
-  if (idx >= 0) cudaEventRecord(ctx->prof[(size_t)idx].stop, ctx->stream);
+  if (idx < 0) return;
+  if (ctx->prof[(size_t)idx].slot >= 0)
+    ctx->cur_stamp = nullptr;
+  else
+    cudaEventRecord(ctx->prof[(size_t)idx].stop, ctx->stream);
 }
 
 namespace {
@@ -101,15 +117,35 @@ int spk_abi_version(void) { return SPK_ABI_VERSION; }
 
 static void prof_clear(spk_ctx* ctx) {
   for (auto& r : ctx->prof) {
-    cudaEventDestroy(r.start);
-    cudaEventDestroy(r.stop);
+    if (r.start) cudaEventDestroy(r.start);
+    if (r.stop) cudaEventDestroy(r.stop);
   }
   ctx->prof.clear();
+  ctx->cur_stamp = nullptr;
+}
+
+static int stamps_reset(spk_ctx* ctx) {
+  if (!ctx->d_stamps) SPK_CUDA_OK(ctx, cudaMalloc(&ctx->d_stamps, 2 * (size_t)kStampCapHost * sizeof(unsigned long long)));
+  SPK_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_stamps, 0xFF, (size_t)kStampCapHost * sizeof(unsigned long long), ctx->stream));
+  SPK_CUDA_OK(ctx, cudaMemsetAsync(ctx->d_stamps + kStampCapHost, 0, (size_t)kStampCapHost * sizeof(unsigned long long), ctx->stream));
+  return SPK_OK;
+}
+
+int spk_profile_mode(spk_ctx* ctx, int mode) {
+  if (!ctx || (mode != SPK_PROFILE_EVENTS && mode != SPK_PROFILE_STAMPS)) return fail(ctx, SPK_ERR_INVALID, "spk_profile_mode: bad arguments");
+  if (ctx->profiling) return fail(ctx, SPK_ERR_STATE, "spk_profile_mode: a profiling pass is running");
+  ctx->prof_mode = mode;
+  return SPK_OK;
 }
 
 int spk_profile_begin(spk_ctx* ctx) {
   if (!ctx) return fail(nullptr, SPK_ERR_INVALID, "spk_profile_begin: null context");
   prof_clear(ctx);
+  if (ctx->prof_mode == SPK_PROFILE_STAMPS) {
+    SPK_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    int rc = stamps_reset(ctx);
+    if (rc) return rc;
+  }
   ctx->profiling = true;
   return SPK_OK;
 }
@@ -133,21 +169,41 @@ int spk_profile_read(spk_ctx* ctx, double ms[SPK_PROF_CATEGORIES], double flops[
   }
   int64_t pos = 0;
   if (detail && detail_cap > 0) detail[0] = 0;
+  std::vector<unsigned long long> st;
+  if (ctx->prof_mode == SPK_PROFILE_STAMPS && ctx->d_stamps && !ctx->prof.empty()) {
+    st.resize(2 * (size_t)kStampCapHost);
+    SPK_CUDA_OK(ctx, cudaMemcpy(st.data(), ctx->d_stamps, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  unsigned long long prev_end = 0;
   for (auto& r : ctx->prof) {
     float t = 0.f;
-    SPK_CUDA_OK(ctx, cudaEventElapsedTime(&t, r.start, r.stop));
+    char span[48] = "";
+    if (r.slot >= 0) {
+      const unsigned long long t0 = st[(size_t)r.slot], t1 = st[(size_t)kStampCapHost + (size_t)r.slot];
+      if (t1 == 0 || t0 == ~0ull) continue;  // a kernel without stamps: its time goes to the next stamped launch
+      const unsigned long long from = prev_end > t0 ? prev_end : t0;
+      t = t1 > from ? (float)((double)(t1 - from) * 1e-6) : 0.f;
+      snprintf(span, sizeof span, " |span_ms=%.6f", (double)(t1 - t0) * 1e-6);
+      prev_end = t1 > prev_end ? t1 : prev_end;
+    } else {
+      SPK_CUDA_OK(ctx, cudaEventElapsedTime(&t, r.start, r.stop));
+    }
     const int c = (r.category >= 0 && r.category < SPK_PROF_CATEGORIES) ? r.category : SPK_PROF_CATEGORIES - 1;
     ms[c] += t;
     flops[c] += r.flops;
     bytes[c] += r.bytes;
     launches[c] += 1;
     if (detail && pos < detail_cap - 1) {
-      int m = snprintf(detail + pos, (size_t)(detail_cap - pos), "%d %.6f %.6g %.6g %s\n", c, (double)t, r.flops, r.bytes,
-                       r.what.c_str());
+      int m = snprintf(detail + pos, (size_t)(detail_cap - pos), "%d %.6f %.6g %.6g %s%s\n", c, (double)t, r.flops, r.bytes,
+                       r.what.c_str(), span);
       if (m > 0) pos += (m < detail_cap - pos) ? m : (detail_cap - pos - 1);
     }
   }
   prof_clear(ctx);
+  if (ctx->prof_mode == SPK_PROFILE_STAMPS && ctx->profiling) {
+    int rc = stamps_reset(ctx);
+    if (rc) return rc;
+  }
   return SPK_OK;
 }
 

@@ -196,6 +196,7 @@ int spk_destroy(spk_ctx* ctx) try {
   cudaStreamSynchronize(ctx->stream);
   net_free(ctx->net);
   if (ctx->d_faults) cudaFree(ctx->d_faults);
+  if (ctx->d_stamps) cudaFree(ctx->d_stamps);
   if (ctx->d_default_lut) cudaFree(ctx->d_default_lut);
   if (ctx->d_big_list) cudaFree(ctx->d_big_list);
   if (ctx->d_big_count) cudaFree(ctx->d_big_count);

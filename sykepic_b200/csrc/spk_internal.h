@@ -26,7 +26,8 @@ namespace spk {
 // one timed launch (profiling mode only): CUDA events on the context's stream around the launch
 struct ProfRec {
   int category;
-  cudaEvent_t start, stop;
+  cudaEvent_t start, stop;  // event mode
+  int slot;                 // stamp mode: index into spk_ctx::d_stamps (-1 in event mode)
   double flops, bytes;
   std::string what;
 };
@@ -47,6 +48,9 @@ struct spk_ctx {
   spk::Net* net = nullptr;
   int sm_count = 148;
   bool profiling = false;
+  int prof_mode = 0;                          // SPK_PROFILE_EVENTS / SPK_PROFILE_STAMPS
+  unsigned long long* d_stamps = nullptr;     // [2 * kStampCap]: start stamps, then end stamps
+  unsigned long long* cur_stamp = nullptr;    // slot of the launch being issued (stamp mode, inside a ProfScope), else null
   std::vector<spk::ProfRec> prof;
 };
 

@@ -72,6 +72,7 @@ struct StemTParams {
   int ring_pitch, region;  // bytes per ring row (128 per pooled column); bytes of the ring / (row buffer + strip) region
   int rb_bytes;            // bytes of the row buffer (rounded to 128): the strip follows it
   int use_tma;
+  unsigned long long* stamp;  // profiling (stamp mode): global-timer slot of this launch, else nullptr
 };
 
 __device__ __forceinline__ uint64_t smem_desc_interleaved(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
   pdl_trigger();
+  stamp_begin(p.stamp);
   pdl_wait();  // the strip is the previous kernel's output
   const int image = blockIdx.x / p.strips;
   const int strip = blockIdx.x - image * p.strips;
@@ -389,6 +391,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  stamp_end(p.stamp);
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kSlots * 128);
@@ -474,6 +477,7 @@ int launch_stem_pool_t(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, co
   }
   const size_t smem = 128 + (size_t)kERows * p.e_pitch + kWBytes + (size_t)p.region + 8 * (kEGroups + 2 * kSlots + 3 + 2 * kRing) + 16;
   SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.stamp = ctx->cur_stamp;
   SPK_CUDA_OK(ctx, launch_pdl(stem_pool_t_kernel, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   SPK_LAUNCH_CHECK(ctx);
   return SPK_OK;

@@ -196,6 +196,23 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// ---- in-kernel time stamps (profiling mode SPK_PROFILE_STAMPS; `s` is null otherwise): the earliest CTA start and the latest
+// CTA end of a launch on the GPU's global nanosecond timer.  Unlike CUDA events between launches these do not serialise the
+// stream, so programmatic dependent launch keeps overlapping kernels while their in-step times are measured.
+constexpr int kStampCap = 8192;  // launches per profiling pass; end stamps live kStampCap slots after the start stamps
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stamp_begin(unsigned long long* s) {
+  if (s != nullptr && threadIdx.x == 0) atomicMin(s, global_ns());
+}
+// call after the CTA's last barrier (every warp has finished its work)
+__device__ __forceinline__ void stamp_end(unsigned long long* s) {
+  if (s != nullptr && threadIdx.x == 0) atomicMax(s + kStampCap, global_ns());
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

@@ -360,7 +360,10 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ per-kernel timing
-    def profile_begin(self):
+    def profile_begin(self, stamps=False):
+        """Per-launch timing on: CUDA events around every launch, or (`stamps`) in-kernel global-timer stamps that leave the
+        launches back to back (programmatic dependent launch keeps overlapping) and report IN-STEP times."""
+        self._ck(self.lib.spk_profile_mode(self.ctx, 1 if stamps else 0))
         self._ck(self.lib.spk_profile_begin(self.ctx))
 
     def profile_read(self, detail=False):

@@ -57,3 +57,43 @@ def merge_processed(local_set, group=None):
     for p in parts:
         out |= set(p)
     return out
+
+
+def gpu_numa_cpus(device):
+    """CPUs of the NUMA node GPU `device` hangs off (sysfs: the PCI device's numa_node -> that node's cpulist), or None when
+    the box does not say (single node, virtualised PCI topology)."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus or None
+    except Exception:  # noqa: BLE001 -- placement is an optimisation, never an error
+        return None
+
+
+def pin_to_gpu_node(device):
+    """Restrict this PROCESS (its loader / writer threads, its pinned allocations by first touch) to the CPUs of the GPU's
+    NUMA node, within what it is allowed already ("watch NUMA placement and PCIe root sharing").  Only for the
+    one-process-per-GPU modes (torchrun ranks, the spawned shard workers of `probability.main`); returns the CPU set or None.
+    SYKEPIC_NO_PIN=1 leaves the affinity alone."""
+    if os.environ.get("SYKEPIC_NO_PIN"):
+        return None
+    cpus = gpu_numa_cpus(device)
+    if not cpus:
+        return None
+    try:
+        allowed = os.sched_getaffinity(0) & cpus
+        if len(allowed) >= 4:  # never squeeze the host pipeline onto a sliver of cores
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except (AttributeError, OSError):
+        pass
+    return None

@@ -8,6 +8,7 @@ import numpy as np
 
 from sykepic_b200 import synth
 
+ROOT_DIR = Path(__file__).resolve().parent.parent
 GOLDEN = Path(__file__).resolve().parent / "golden"
 FIXTURE = GOLDEN / "ref_fixture"
 VALID_BIN = "D20180712T065600_IFCB114"

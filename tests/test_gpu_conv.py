@@ -197,8 +197,6 @@ def test_fused_stem_matches_unfused_and_torch(ctx, t, n):
 def test_fused_downsample_shortcut(ctx, t, n, c1, c2):
     """A ResNet stage entry: the 1x1 / stride-2 shortcut fused into the 3x3 / stride-2 convolution's kernel (second
     accumulator on the centre tap) against the two separate launches and a torch fp32 reference."""
-    import os
-
     import torch
     import torch.nn.functional as F
 
@@ -212,21 +210,23 @@ def test_fused_downsample_shortcut(ctx, t, n, c1, c2):
     lib = ctx.lib
 
     def run(fused):
-        if fused:
-            os.environ.pop("SPK_NO_DS_FUSION", None)
-        else:
-            os.environ["SPK_NO_DS_FUSION"] = "1"
-        try:
-            ctx.ck(lib.spk_net_begin(ctx.ctx, t, t, 1, _lib.PRECISION_BF16, n))
-            ctx.ck(lib.spk_net_conv(ctx.ctx, 0, 0, 1, 0, -1, w1.ctypes.data, c1, 1, 3, 3, 1, 1, None, None, None, None, BN_EPS, None, 1, _lib.CONV_SIMT))
+        # the fusion pass matches "shortcut declared directly before its 3x3" (the order engine.py emits); declaring the
+        # 3x3 first keeps the two convolutions separate launches
+        ctx.ck(lib.spk_net_begin(ctx.ctx, t, t, 1, _lib.PRECISION_BF16, n))
+        ctx.ck(lib.spk_net_conv(ctx.ctx, 0, 0, 1, 0, -1, w1.ctypes.data, c1, 1, 3, 3, 1, 1, None, None, None, None, BN_EPS, None, 1, _lib.CONV_SIMT))
+
+        def shortcut():
             ctx.ck(lib.spk_net_conv(ctx.ctx, 1, 0, 3, 0, -1, wd.ctypes.data, c2, c1, 1, 1, 2, 0, None, None, None, None, BN_EPS, bd.ctypes.data, 0, _lib.CONV_TCGEN05))
+
+        def conv3():
             ctx.ck(lib.spk_net_conv(ctx.ctx, 1, 0, 2, 0, -1, w3.ctypes.data, c2, c1, 3, 3, 2, 1, None, None, None, None, BN_EPS, b3.ctypes.data, 1, _lib.CONV_TCGEN05))
-            hw = np.zeros((4, c2), np.float32)
-            hb = np.zeros(4, np.float32)
-            ctx.ck(lib.spk_net_head(ctx.ctx, 2, 1, (C.c_void_p * 1)(hw.ctypes.data), (C.c_void_p * 1)(hb.ctypes.data), (C.c_int * 2)(c2, 4)))
-            ctx.ck(lib.spk_net_end(ctx.ctx))
-        finally:
-            os.environ.pop("SPK_NO_DS_FUSION", None)
+
+        for op in ((shortcut, conv3) if fused else (conv3, shortcut)):
+            op()
+        hw = np.zeros((4, c2), np.float32)
+        hb = np.zeros(4, np.float32)
+        ctx.ck(lib.spk_net_head(ctx.ctx, 2, 1, (C.c_void_p * 1)(hw.ctypes.data), (C.c_void_p * 1)(hb.ctypes.data), (C.c_int * 2)(c2, 4)))
+        ctx.ck(lib.spk_net_end(ctx.ctx))
         launches0 = lib.spk_launch_count(ctx.ctx)
         with torch.cuda.device(ctx.device), torch.cuda.stream(ctx.stream):
             x = torch.from_numpy(img).to(ctx.device)
