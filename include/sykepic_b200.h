@@ -50,7 +50,7 @@ extern "C" {
 /* ---- enums -------------------------------------------------------------------------- */
 enum { SPK_BORDER_MODE = 0, SPK_BORDER_BLACK = 1, SPK_BORDER_WHITE = 2 }; /* sykepic/train/image.py:20-28 */
 enum { SPK_DTYPE_F32 = 0, SPK_DTYPE_BF16 = 1, SPK_DTYPE_U8 = 2,
-       SPK_DTYPE_SPLIT = 3 /* internal activation format of the FP32 precision: bf16 hi | bf16 lo in one 32-bit word */ };
+       SPK_DTYPE_SPLIT = 3 /* internal activation format of the FP32_TC precision: fp16 hi | fp16 lo in one 32-bit word */ };
 enum { SPK_LAYOUT_NCHW = 0, SPK_LAYOUT_NHWC = 1 };
 enum { SPK_PRECISION_FP32 = 0, SPK_PRECISION_BF16 = 1,
        SPK_PRECISION_FP32_TC = 2 /* fp32-level accuracy on the bf16 tensor cores (activations and weights as bf16 hi + lo;

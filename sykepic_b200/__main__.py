@@ -31,7 +31,8 @@ def build_parser():
                              help="Accepted for compatibility (no loader processes on this path)")
     prob_parser.add_argument("-f", "--force", action="store_true", help="Force overwrite of previous probabilities")
     prob_parser.add_argument("--precision", choices=("fp32", "fp32_tc", "bf16"), default=None,
-                             help="fp32 (default; within 1e-4 of the reference) or bf16 tensor cores (within 2e-2)")
+                             help="fp32_tc (default: fp32-level accuracy on the tensor cores, within 1e-4 of the reference), "
+                                  "fp32 (exact CUDA-core path) or bf16 tensor cores (within 2e-2)")
     prob_parser.add_argument("--gpus", dest="devices", type=int, default=None, metavar="N",
                              help="Shard bins over the first N GPUs of this box (default 1)")
 

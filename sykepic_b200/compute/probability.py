@@ -38,7 +38,9 @@ EvalParams = namedtuple(
     "EvalParams",
     ["batch_size", "num_workers", "classes", "img_shape", "transform", "device"],
 )
-DEFAULT_PRECISION = os.environ.get("SYKEPIC_PRECISION", "fp32")
+# "fp32_tc": fp32-level accuracy (within 1e-4 of the reference, measured <= 2e-5) on the tcgen05 tensor cores; "fp32" = the
+# exact CUDA-core FFMA path (<= 1e-6, ~7x slower); "bf16" = within 2e-2, ~4x faster again
+DEFAULT_PRECISION = os.environ.get("SYKEPIC_PRECISION", "fp32_tc")
 
 
 ROI_FILE_LIMIT = 1e9  # bins whose `.roi` is larger are not processed (probability.py:45-51)

@@ -24,7 +24,10 @@
 //     the MMAs of tile i+1.
 #include <cuda.h>
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "spk_internal.h"
@@ -54,6 +57,9 @@ struct alignas(64) TcParams {
   int tiles_w, tiles_h, tiles_img, tiles_n;
   int taps, kchunks, cin_pad;
   int total_tiles;
+  int split_chunk;  // kModeSplit: k blocks per accumulation chunk (kSplitChunk)
+  const float* wscale;         // kModeSplit: 2^-k(o) per output channel, undoes the power-of-two scaling of the fp16 weights
+  unsigned long long* faults;  // kModeSplit: counts tiles with an output beyond the fp16 range of the SplitF format
   int reverse;  // walk the tiles last-to-first (see conv_hp.cu)
   // kModePre: y = conv(relu(x * pre_scale[c] + pre_shift[c])): DenseNet's pre-activation BatchNorm + ReLU applied to the A
   // tiles in shared memory (every consumer of a concatenation has its own BatchNorm, so it cannot be folded into a producer)
@@ -187,12 +193,21 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 }
 
 // MODE 0: plain.  MODE 1 (kModeDs): a second weight tile on the centre tap feeds a second accumulator (fused 1x1 / stride-2
-// shortcut).  MODE 2 (kModeSplit): FP32-accurate convolution on the bf16 tensor cores.  Activations are stored as SplitF
-// words -- bf16 hi in the low half, bf16 lo = bf16(x - hi) in the high half -- which the MMA sees as a bf16 tensor with
+// shortcut).  MODE 2 (kModeSplit): FP32-accurate convolution on the 16-bit tensor cores.  Activations are stored as SplitF
+// words -- fp16 hi in the low half, fp16 lo = fp16(x - hi) in the high half -- which the MMA sees as an fp16 tensor with
 // twice the channels, K index 2c = hi_c, 2c + 1 = lo_c.  Every k block is multiplied by TWO weight tiles into the same
 // accumulator: [w_hi, w_hi] (gives x_hi*w_hi + x_lo*w_hi) and [w_lo, w_lo] (x_hi*w_lo + x_lo*w_lo): the full 16-bit x
 // 16-bit product with fp32 accumulation (torch emulation of ResNet-18: |dp| <= 5e-6, experiments/emul_bf16x3_split.py).
 constexpr int kModePlain = 0, kModeDs = 1, kModeSplit = 2, kModePre = 3;
+// kModeSplit: k blocks accumulated in TMEM before the epilogue takes the partial sum over.  The tensor core TRUNCATES every
+// fp32 accumulation (one per K = 16 MMA): a bias of ~half an ulp of the running sum per addition, which grows linearly with
+// K (rms error 4e-6 at 72 additions, 1e-5 at 576).  With 4 k blocks = 16 additions per accumulator the bias stays below
+// ~8 ulp of a PARTIAL sum, and the partial sums are added in registers with round-to-nearest fp32 adds.  Measured on
+// the three benchmark checkpoints (max |dp| against the reference, ResNet-18 / -50 / DenseNet-121, fp16 hi + lo operands):
+// no chunking 7.1e-5 / 7.0e-6 / 4.4e-5, 8 blocks 1.4e-5 / 4.5e-6 / 2.1e-5, 2 blocks 6.1e-6 / 4.8e-6 / 1.4e-5
+// at 67 / 64 / 54 k ROI/s (ResNet-18); with bf16 hi + lo operands (16 significant bits) the floor was 5e-5 .. 1e-4
+// whatever the chunk.
+constexpr int kSplitChunk = 4;
 constexpr int kPreWarps = 8;                      // kModePre: transform warps 6..13
 constexpr int kThreadsPre = kThreads + 32 * kPreWarps;
 constexpr int kPreTable = 2 * 1024 * 4;           // scale | shift for up to 1024 input channels
@@ -209,7 +224,8 @@ struct Cfg {
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + (MODE == kModePre ? kPreTable : 0);
   // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10),
   // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
-  static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  // (kModeSplit: A = B = fp16, format 0)
+  static constexpr uint32_t kIdesc = (1u << 4) | (MODE == kModeSplit ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 };
 
 template <int BN, int MODE>
@@ -316,10 +332,16 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::kAccCols);
+        uint32_t d_tmem = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
+          // an accumulation chunk: the whole tile, or kSplitChunk k blocks in split mode
+          const bool chunk_start = SPLIT ? (kb % p.split_chunk == 0) : (kb == 0);
+          const bool chunk_end = kb + 1 == kblocks || (SPLIT && (kb % p.split_chunk == p.split_chunk - 1));
+          if (chunk_start) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+            tc_fence_after();
+            d_tmem = tmem_base + (uint32_t)(acc * C::kAccCols);
+          }
           mbar_wait(PRE ? ready_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + stage * C::kStageBytes;
@@ -328,15 +350,14 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (chunk_start && k == 0) ? 0u : 1u);
           }
-          if (SPLIT) {  // the lo weights against the same (hi, lo) activation tile.  Own accumulator: the tensor core TRUNCATES every
-                        // fp32 accumulation (measured: rms error 4e-6 at K = 576 growing to 2e-5 at K = 4608), and these small
-                        // terms would double the number of additions into the large sum
+          if (SPLIT) {  // the lo weights against the same (hi, lo) activation tile, into their own accumulator (these small
+                        // terms would double the number of truncating additions into the large sum)
             const uint64_t b2_desc = smem_desc_sw128(sa + kABytes + C::kBBytes);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              tc_mma_w(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), C::kIdesc, (kb | k) != 0 ? 1u : 0u);
+              tc_mma_w(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), C::kIdesc, (chunk_start && k == 0) ? 0u : 1u);
           }
           if (DS) {
             // the centre tap of a 3x3 / stride 2 / pad 1 filter samples exactly the pixels a 1x1 / stride 2
@@ -355,11 +376,13 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
             stage = 0;
             phase ^= 1u;
           }
-        }
-        tc_commit_w(tfull_bar(acc));  // accumulator complete
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
+          if (chunk_end) {
+            tc_commit_w(tfull_bar(acc));  // accumulator (chunk) complete
+            if (++acc == 2) {
+              acc = 0;
+              acc_phase ^= 1u;
+            }
+          }
         }
       }
     }
@@ -425,8 +448,10 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
       const int wo = twi * p.wb + wbi, ho = thi * p.hb + hbi, img = ng * p.nb + nbi;
       const bool valid = (wo < p.wo) && (ho < p.ho) && (img < p.n);
       const long long pix = ((long long)img * p.ho + ho) * p.wo + wo;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
+      if constexpr (!SPLIT) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+      }
       // one pass over BN accumulator columns: + bias (+ residual) (ReLU) -> bf16 -> 16-byte stores of the pixel's row
       auto drain = [&](uint32_t taddr, const float* brow, const __nv_bfloat16* rrow, __nv_bfloat16* yrow, bool relu) {
 #pragma unroll 1
@@ -478,49 +503,65 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
           __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
         }
       };
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols);
       if constexpr (SPLIT) {
-        // SplitF in / out: one 32-bit word per channel (ldy / ldres count words)
+        // SplitF in / out: one 32-bit word per channel (ldy / ldres count words).  The accumulation chunks of the tile arrive
+        // one after the other; their partial sums (hi-weight + lo-weight accumulator) are added up here in registers
         const uint32_t* rrow = p.res ? reinterpret_cast<const uint32_t*>(p.res) + pix * p.ldres + nt * BN : nullptr;
         uint32_t* yrow = reinterpret_cast<uint32_t*>(p.y) + pix * p.ldy + nt * BN;
         const float* brow = p.bias + nt * BN;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32], vl[32];
-          tmem_ld32(taddr + (uint32_t)c, v);
-          tmem_ld32(taddr + (uint32_t)(BN + c), vl);
-          tmem_ld_wait();
-          if (valid) {
+        float part[BN];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c + j));
-              float f[4] = {(__uint_as_float(v[j]) + __uint_as_float(vl[j])) + b4.x, (__uint_as_float(v[j + 1]) + __uint_as_float(vl[j + 1])) + b4.y,
-                            (__uint_as_float(v[j + 2]) + __uint_as_float(vl[j + 2])) + b4.z, (__uint_as_float(v[j + 3]) + __uint_as_float(vl[j + 3])) + b4.w};
-              if (rrow) {
-                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c + j));
-                f[0] += split_load(r4.x);
-                f[1] += split_load(r4.y);
-                f[2] += split_load(r4.z);
-                f[3] += split_load(r4.w);
-              }
-              if (p.relu) {
+        for (int c = 0; c < BN; ++c) part[c] = 0.f;
+        const int nchunks = (kblocks + p.split_chunk - 1) / p.split_chunk;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) f[e] = fmaxf(f[e], 0.f);
-              }
-              *reinterpret_cast<uint4*>(yrow + c + j) = make_uint4(split_store(f[0]), split_store(f[1]), split_store(f[2]), split_store(f[3]));
-            }
+          for (int c = 0; c < BN; c += 16) {
+            uint32_t v[16], vl[16];
+            tc::tmem_ld16(taddr + (uint32_t)c, v);
+            tc::tmem_ld16(taddr + (uint32_t)(BN + c), vl);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) part[c + j] += __uint_as_float(v[j]) + __uint_as_float(vl[j]);
           }
+          tc_fence_before();
           __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
         }
-        tc_fence_before();
+        bool ovf = false;
+        if (valid) {
+          const float* srow = p.wscale + nt * BN;
+#pragma unroll
+          for (int c = 0; c < BN; c += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(srow + c));  // powers of two: exact
+            float f[4] = {fmaf(part[c], s4.x, b4.x), fmaf(part[c + 1], s4.y, b4.y), fmaf(part[c + 2], s4.z, b4.z), fmaf(part[c + 3], s4.w, b4.w)};
+            if (rrow) {
+              const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rrow + c));
+              f[0] += split_load(r4.x);
+              f[1] += split_load(r4.y);
+              f[2] += split_load(r4.z);
+              f[3] += split_load(r4.w);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            ovf |= !(fmaxf(fmaxf(fabsf(f[0]), fabsf(f[1])), fmaxf(fabsf(f[2]), fabsf(f[3]))) <= kSplitMax);  // (also catches NaN)
+            *reinterpret_cast<uint4*>(yrow + c) = make_uint4(split_store(f[0]), split_store(f[1]), split_store(f[2]), split_store(f[3]));
+          }
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
-        }
+        if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicAdd(p.faults, 1ULL);
         continue;
       }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols);
       drain(taddr, p.bias + nt * BN, p.res ? p.res + pix * p.ldres + nt * BN : nullptr, p.y + pix * p.ldy + nt * BN, p.relu != 0);
       if (DS) drain(taddr + (uint32_t)BN, p.bias2 + nt * BN, nullptr, p.y2 + pix * p.ldy2 + nt * BN, false);
       tc_fence_before();
@@ -576,6 +617,7 @@ struct TcConvPlan {
   TcParams prm;
   __nv_bfloat16* d_w = nullptr;
   __nv_bfloat16* d_w2 = nullptr;
+  float* d_wscale = nullptr;  // split plans
   int64_t bytes = 0;
   const void* x_ptr = nullptr;
   int n_maps = 0;
@@ -678,6 +720,7 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
   prm.relu = g.relu;
   prm.taps = g.kh * g.kw;
   prm.kchunks = (g.cin + kBK - 1) / kBK;
+  prm.split_chunk = debug_env("SPK_SPLIT_CHUNK") ? std::max(1, atoi(debug_env("SPK_SPLIT_CHUNK"))) : kSplitChunk;
   prm.cin_pad = prm.kchunks * kBK;
   prm.tiles_n = g.cout / p->bn;
 
@@ -730,20 +773,39 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
   std::vector<__nv_bfloat16> wb16((size_t)g.cout * kk, __float2bfloat16(0.f));
   // plain round-to-nearest: error-diffusion rounding along K was tried and measured (torch emulation of the
   // whole network, ResNet-18 and -50 checkpoints): no robust gain, worse for 1x1 layers.
-  std::vector<__nv_bfloat16> wlo;
+  std::vector<__nv_bfloat16> wlo;  // (split plans: both buffers hold fp16 bit patterns)
+  std::vector<float> wscale;
   if (p->split) {
-    // [w_hi, w_hi] / [w_lo, w_lo] over the interleaved K index 2c + e
+    // [w_hi, w_hi] / [w_lo, w_lo] over the interleaved K index 2c + e, fp16 of w * 2^k(o): 2^k(o) brings the channel's largest
+    // weight into [2^13, 2^14), so that hi AND lo are normal fp16 numbers for every weight above 1e-5 of the largest
+    // (22 significant bits); the epilogue multiplies the accumulator by 2^-k(o)
     wlo.assign(wb16.size(), __float2bfloat16(0.f));
-    for (int o = 0; o < g.cout; ++o)
+    wscale.assign((size_t)g.cout, 1.f);
+    uint16_t* whi_bits = reinterpret_cast<uint16_t*>(wb16.data());
+    uint16_t* wlo_bits = reinterpret_cast<uint16_t*>(wlo.data());
+    for (int o = 0; o < g.cout; ++o) {
+      double amax = 0.0;
+      for (size_t i = 0; i < (size_t)prm.taps * cin_logical; ++i) amax = std::max(amax, std::fabs((double)w[(size_t)o * prm.taps * cin_logical + i]));
+      int k = 0;
+      if (amax > 0.0 && std::isfinite(amax)) {
+        int e;
+        std::frexp(amax, &e);  // amax = m * 2^e, m in [0.5, 1)
+        k = std::max(-100, std::min(100, 14 - e));
+      }
+      wscale[(size_t)o] = (float)std::ldexp(1.0, -k);
       for (int t = 0; t < prm.taps; ++t)
         for (int c = 0; c < cin_logical; ++c) {
-          const float v = w[((size_t)o * prm.taps + t) * cin_logical + c];
-          const __nv_bfloat16 hi = __float2bfloat16(v);
-          const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+          const float v = (float)std::ldexp((double)w[((size_t)o * prm.taps + t) * cin_logical + c], k);
+          const __half hi = __float2half_rn(v);
+          const __half lo = __float2half_rn(v - __half2float(hi));
+          uint16_t hb, lb;
+          memcpy(&hb, &hi, 2);
+          memcpy(&lb, &lo, 2);
           const size_t at = (size_t)o * kk + (size_t)t * prm.cin_pad + 2 * c;
-          wb16[at] = wb16[at + 1] = hi;
-          wlo[at] = wlo[at + 1] = lo;
+          whi_bits[at] = whi_bits[at + 1] = hb;
+          wlo_bits[at] = wlo_bits[at + 1] = lb;
         }
+    }
   } else
   for (int o = 0; o < g.cout; ++o)
     for (int t = 0; t < prm.taps; ++t)
@@ -772,6 +834,10 @@ int tc_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, con
   if (p->split) {
     cudaError_t e2 = cudaMalloc(&p->d_w2, wlo.size() * 2);
     if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_w2, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&p->d_wscale, wscale.size() * 4);
+    if (e2 == cudaSuccess) e2 = cudaMemcpy(p->d_wscale, wscale.data(), wscale.size() * 4, cudaMemcpyHostToDevice);
+    prm.wscale = p->d_wscale;
+    prm.faults = ctx->d_faults;
     if (e2 != cudaSuccess) {
       tc_conv_plan_destroy(p);
       return fail(ctx, SPK_ERR_CUDA, "tcgen05 convolution: lo weight upload: %s", cudaGetErrorString(e2));
@@ -841,6 +907,7 @@ void tc_conv_plan_destroy(TcConvPlan* p) {
   if (!p) return;
   if (p->d_w) cudaFree(p->d_w);
   if (p->d_w2) cudaFree(p->d_w2);
+  if (p->d_wscale) cudaFree(p->d_wscale);
   delete p;
 }
 

@@ -837,10 +837,8 @@ int spk_net_read_buffer(spk_ctx* ctx, int buf, int64_t n, float* host_out, int64
     std::vector<uint32_t> tmp((size_t)elems);
     SPK_CUDA_OK(ctx, cudaMemcpy(tmp.data(), b->d, (size_t)elems * 4, cudaMemcpyDeviceToHost));
     for (int64_t i = 0; i < elems; ++i) {
-      const uint32_t hi = tmp[(size_t)i] << 16, lo = tmp[(size_t)i] & 0xffff0000u;
-      float fh, fl;
-      memcpy(&fh, &hi, 4);
-      memcpy(&fl, &lo, 4);
+      const float fh = __half2float(__ushort_as_half((unsigned short)(tmp[(size_t)i] & 0xffffu)));
+      const float fl = __half2float(__ushort_as_half((unsigned short)(tmp[(size_t)i] >> 16)));
       host_out[i] = fh + fl;
     }
   } else {

@@ -73,6 +73,7 @@ struct StemParams {
   int groups, rb_pitch;  // 16-pixel groups per strip row that are converted to bf16; byte pitch of the bf16 row buffer
   long long* trace;      // debug: clock64 timestamps of a few CTAs (SPK_STEM_TRACE=1), else nullptr
   int use_tma;           // strip staged by one TMA box (tw % 16 == 0, tw <= 224); else by the builder threads
+  unsigned long long* faults;  // kSplit: counts CTAs with an output beyond the fp16 range of the SplitF format
 };
 
 // no-swizzle K-major descriptor: rows 16 B apart inside an 8-row core matrix, SBO between core matrices
@@ -132,9 +133,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 #define STEM_TRACE(slot) do { } while (0)
 #endif
 
-// kSplit: the output is SplitF words (bf16 hi | lo, FP32_TC precision) instead of bf16: the accumulators already carry
-// fp32 accuracy (exact bf16 pixels x bf16 hi + lo weights); only the pool buffers double (one CTA per SM then).
-// kHalf (bf16 output only): pixels and weights in fp16, ONE pass over K = 64.  The weights of channel c are scaled by a
+// kSplit (with kHalf): the output is SplitF words (fp16 hi | lo, FP32_TC precision) instead of bf16: the accumulators carry
+// fp32 accuracy (exact fp16 pixels x per-channel scaled fp16 hi + lo weights, TWO passes); the pool buffers double (one
+// CTA per SM then).
+// kHalf: pixels and weights in fp16; for bf16 output ONE pass over K = 64.  The weights of channel c are scaled by a
 // power of two into the top of the fp16 range (exact) and the sums scaled back in the epilogue's FFMA; an fp16 weight
 // is good to 2^-12 relative, eight times finer than the bf16 rounding of the output, so the second (lo) pass buys
 // nothing there -- and it was half of the kernel's MMA shared-memory traffic (48 KB per conv row).
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
       mbar_init_fence();
       // weight tile (16 KB, bulk copy) and, when the geometry allows, the u8 strip as ONE TMA box: pixel x of
       // input row y lands at img[(y - y_base) * pitch + x + kXOff]; out-of-image rows / columns are zero-filled
-      constexpr uint32_t kWBytes = kHalf ? kBTile : kBBytes;
+      constexpr uint32_t kWBytes = (kHalf && !kSplit) ? kBTile : kBBytes;  // (split: fp16 hi AND lo tiles)
       mbar_expect_tx(load_bar, kWBytes + (p.use_tma ? (uint32_t)(kERows * p.pitch) : 0u));
       bulk_load(base + b_off, p.w_il, kWBytes, load_bar);
       // (the box must start on a 16-byte boundary of the row: x = -16, not -3)
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
         // K = 128: the eight 16-byte K chunks (filter rows) against the hi weights, then again against the lo weights
         // (kHalf: one pass, fp16 operands)
 #pragma unroll
-        for (int pass = 0; pass < (kHalf ? 1 : 2); ++pass)
+        for (int pass = 0; pass < ((kHalf && !kSplit) ? 1 : 2); ++pass)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_w(d, smem_desc_interleaved(a_s + 2u * k * kERowBytes, kERowBytes, 128),
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
     // 2p-1 (the row that closed the previous window) is READ AGAIN from its accumulator slot, which is only released now;
     // odd row 2p+1: acc = max(acc, row 2p+1), emit.  (Restarting the running maximum from registers instead cost a
     // predicated move and a PLOP3 per element and row: 4 k of the 27 k instructions of a strip.)
+    bool ovf = false;
     for (int idx = 0; idx < n_rows; ++idx) {
       const int i = c_lo + idx, slot = idx % kSlots;
       const bool odd = (i & 1) != 0;
@@ -372,7 +375,9 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const int e = qc * 16 + c * 8 + h2 * 4 + j;
-                  o[j] = split_store(fmaxf(acc[e] + bias_sm[half * 32 + e], 0.f));
+                  const float v = fmaxf(fmaf(acc[e], bias_sm[64 + half * 32 + e], bias_sm[half * 32 + e]), 0.f);  // x 2^-k(channel): exact
+                  ovf |= (wo < p.wc) && !(v <= kSplitMax);  // (columns beyond the image hold junk)
+                  o[j] = split_store(v);
                 }
                 const int chunk = 8 * half + 4 * qc + 2 * c + h2;  // 16 chunks of 4 channels per column
                 *reinterpret_cast<uint4*>(pool + wo * kPoolRow + ((chunk ^ (wo & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -451,6 +456,10 @@ __global__ void __launch_bounds__(kThreads, kSplit ? 1 : 2) stem_pool_kernel(con
       }
       if (tid == 160) STEM_TRACE(40 + idx);
     }
+    if constexpr (kSplit) {
+      if (__any_sync(0xffffffffu, ovf) && lane == 0) atomicAdd(p.faults, 1ULL);
+    }
+    (void)ovf;
   }
 
   tc_fence_before();
@@ -497,7 +506,9 @@ int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out, bool spl
   float* inv_scale = reinterpret_cast<float*>(tile.data() + kBBytes / 2);
   for (int o = 0; o < 64; ++o) inv_scale[o] = 1.f;
   const bool half = !split && !stem_hilo_forced();
-  for (int o = 0; half && o < 64; ++o) {
+  // fp16 weights scaled per channel by a power of two (largest weight into [2^13, 2^14)); `half`: one tile, 2^-12 relative;
+  // `split` (FP32_TC): hi + lo tiles, 22 significant bits, both normal fp16 numbers
+  for (int o = 0; (half || split) && o < 64; ++o) {
     double amax = 0.0;
     for (int t = 0; t < 49; ++t) amax = std::max(amax, std::fabs((double)w[o * 49 + t] / 255.0));
     int k = 0;
@@ -510,13 +521,19 @@ int stem_pool_pack_weights(spk_ctx* ctx, const float* w, uint4** d_out, bool spl
     inv_scale[o] = (float)std::ldexp(1.0, -k);
     for (int r = 0; r < 7; ++r)
       for (int s = 0; s < 7; ++s) {
-        const __half hv = __float2half_rn((float)std::ldexp((double)w[(o * 7 + r) * 7 + s] / 255.0, k));
+        const float v = (float)std::ldexp((double)w[(o * 7 + r) * 7 + s] / 255.0, k);
+        const __half hv = __float2half_rn(v);
         uint16_t b;
         memcpy(&b, &hv, 2);
         tile[(size_t)r * 512 + (size_t)o * 8 + s] = b;
+        if (split) {
+          const __half lv = __float2half_rn(v - __half2float(hv));
+          memcpy(&b, &lv, 2);
+          tile[(size_t)kBTile / 2 + (size_t)r * 512 + (size_t)o * 8 + s] = b;
+        }
       }
   }
-  for (int o = 0; !half && o < 64; ++o)
+  for (int o = 0; !half && !split && o < 64; ++o)
     for (int r = 0; r < 7; ++r)
       for (int s = 0; s < 7; ++s) {
         const float v = (float)((double)w[(o * 7 + r) * 7 + s] / 255.0);
@@ -576,7 +593,7 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
                       8 * (kEGroups + 3 + 2 * kSlots) + 16;
   const bool half = !split && !stem_hilo_forced();  // (must agree with stem_pool_pack_weights)
   if (split)
-    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (half)
     SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else
@@ -585,13 +602,14 @@ int launch_stem_pool(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, cons
   static long long* d_trace = nullptr;
   static int trace_left = 3;
   p.trace = nullptr;
+  p.faults = ctx->d_faults;
   if (want_trace && trace_left > 0) {
     if (!d_trace) cudaMalloc(&d_trace, 16 * 64 * sizeof(long long));
     cudaMemsetAsync(d_trace, 0, 16 * 64 * sizeof(long long), ctx->stream);
     p.trace = d_trace;
   }
   if (split)
-    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<true, false>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
+    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<true, true>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   else if (half)
     SPK_CUDA_OK(ctx, launch_pdl(stem_pool_kernel<false, true>, dim3((unsigned)(n * p.strips)), dim3(kThreads), smem, ctx->stream, cache.map, p));
   else

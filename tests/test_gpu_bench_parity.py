@@ -85,3 +85,24 @@ def test_fp32_gate_at_launch_size_256(model_dirs, case):
     same = np.array([a == b2 and bool(c) == d for a, b2, c, d in zip(names, want["prediction"], classified, want["classified"])])
     assert same.mean() >= 0.999, (case, float(same.mean()))
     print(f"{case} fp32: max |dp| {err.max():.2e}, labels {same.mean():.4f}")
+
+
+@pytest.mark.parametrize("case", list(BIG_CASES))
+def test_fp32_tc_gate_at_launch_size_256(model_dirs, case):
+    """FP32-level accuracy on the tensor cores (precision "fp32_tc", the CLI default): the FP32 gate of 1e-4 and the label
+    gate on the benchmark checkpoints, every layer on tcgen05 (no CUDA-core fallback)."""
+    b, g, labels = _golden(case)
+    eng = engine.Engine(model_dirs(case), precision="fp32_tc", max_batch=256, pre_chunk=4096)
+    try:
+        assert int(eng.lib.spk_net_simt_layers(eng.ctx)) == 0
+        eng.set_thresholds(o_pred.threshold_dictionary(FIXTURE / "thresholds-zero.txt"))
+        rid, probs, label, classified = eng.run_bin(b["adc_text"], b["roi_bytes"], batch_size=256, want_labels=True)
+        names = [eng.spec.classes[i] for i in label]
+    finally:
+        eng.close()
+    err = np.abs(probs - g["probs"]).max(axis=1)
+    print(f"{case} fp32_tc: max |dp| {err.max():.2e}")
+    assert err.max() <= FP32_PROB_TOL, (case, float(err.max()))
+    want = labels["thresholds-zero"]
+    same = np.array([a == b2 and bool(c) == d for a, b2, c, d in zip(names, want["prediction"], classified, want["classified"])])
+    assert same.mean() >= 0.999, (case, float(same.mean()))

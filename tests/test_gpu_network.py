@@ -244,10 +244,40 @@ def test_densenet121_matches_oracle(tmp_path):
             eng.close()
 
 
-@pytest.mark.parametrize("case", ["r18_180", "r18_224n"])
+def test_fp32_tc_overflow_is_loud(model_dirs, tmp_path):
+    """The fp16 hi + lo split format of FP32_TC holds |x| <= 65504.  A checkpoint whose activations leave that range must
+    not produce quiet garbage: the convolution epilogue counts the tile, `.result()` raises; `fp32` runs the same model."""
+    import shutil
+
+    import torch
+
+    src = model_dirs("r18_180")
+    mdir = tmp_path / "huge"
+    shutil.copytree(src, mdir)
+    sd = torch.load(mdir / "best_state.pth", map_location="cpu", weights_only=False)
+    key = next(k for k in sd if k.endswith("weight") and sd[k].ndim == 4 and sd[k].shape[1] in (1, 3))  # the stem convolution
+    sd[key] = sd[key] * 3.0e6
+    torch.save(sd, mdir / "best_state.pth")
+    (bname, b), = case_bins("r18_180")[:1]
+    eng = engine.Engine(mdir, precision="fp32_tc", max_batch=64)
+    try:
+        with pytest.raises(ArithmeticError, match="fp16 range"):
+            eng.run_bin(b["adc_text"], b["roi_bytes"])
+    finally:
+        eng.close()
+    eng = engine.Engine(mdir, precision="fp32", max_batch=64)
+    try:
+        rid, probs = eng.run_bin(b["adc_text"], b["roi_bytes"])
+        assert np.isfinite(probs).all()
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("case", ["r18_180", "r18_224n", "r50_224"])
 def test_fp32_tc_probabilities(engines, case):
     """FP32-level accuracy on the bf16 tensor cores (precision "fp32_tc": bf16 hi + lo activations and weights, fp32
-    accumulation): within the FP32 gate of 1e-4 on ResNet-18, labels identical to the fused rule on its own CSV decimals."""
+    accumulation in chunks of 4 k blocks summed in registers): within the FP32 gate of 1e-4 on ResNet-18 AND ResNet-50,
+    labels identical to the fused rule on its own CSV decimals."""
     eng = engines(case, "fp32_tc")
     eng.set_thresholds(_thresholds("thresholds-zero"))
     for bname, b in case_bins(case):
