@@ -398,6 +398,381 @@ __global__ void __launch_bounds__(kThreads, 2) stem_pool_t_kernel(const __grid_c
   }
 }
 
+// ======================================================================================================================
+// Persistent, pipelined form of the same kernel (the default when the strip can be staged by TMA).
+//
+// stem_pool_t_kernel runs one CTA per strip of 4 pooled rows with its phases one after the other (load, u8 -> fp16, E rows,
+// MMAs, epilogue, stores), two CTAs per SM; 26 input rows are staged and expanded for 16 new ones, 10 conv rows computed
+// for 8 new ones, and the 20 KB weight operand is fetched by each of the 3584 CTAs.  ncu (profiles/r2_ncu_stem_pool_t.txt):
+// 121 us per 256 images, tensor pipe 16.5 %, DRAM 5.9 %, issue slots half empty: latency-bound.
+// Here ONE CTA per SM stays resident and walks over units of kBand = 14 pooled rows (a quarter of a 224 image: 29 conv rows
+// = 15 accumulators for 14 pooled rows), with every role running concurrently on rings of mbarriers:
+//   warp 5       producer: weights once, then the u8 strip of unit i + 1 / i + 2 (one TMA box of 68 rows, double-buffered)
+//   warps 6-9    builders: E rows straight from the u8 strip (8 taps -> fp16, 16 bytes per conv column), one row of every
+//                QUAD (4 E rows = what one accumulator adds to the previous one's window) each, into a ring of 8 quads
+//   warp 4       MMA issuer: accumulator t reads quads t, t + 1 and half of t + 2 of its unit; 5 MMAs; commits publish the
+//                accumulator (ring of 4 TMEM slots) and hand quad t back to the builders
+//   warps 10-25  epilogue, two groups of 8 warps that take alternate accumulators (an accumulator's epilogue is a ~1100-cycle
+//                dependent chain per warp: two in flight), same register-side horizontal max as above, into a ring of 8
+//                conv rows at pooled width
+//   warps 0-3    store warps: vertical max of three ring rows, NHWC stores, ring rows handed back
+// All counters (quads, accumulators, conv rows) run on across units, so the next unit's strip, E rows and MMAs start while
+// the current unit's epilogue and stores drain.
+constexpr int kBand = 14;                      // pooled rows per unit
+constexpr int kMaxAcc = kBand + 1;             // 2 * kBand + 1 conv rows
+constexpr int kStripRowsP = 4 * (kMaxAcc + 2); // input rows staged per unit (E rows 0 .. 4 nacc + 5, rounded to quads)
+constexpr int kQuads = 8;                      // E ring, in quads
+constexpr int kSlotsP = 4;                     // TMEM accumulator ring (4 x 128 columns)
+constexpr int kRingP = 8;                      // conv rows between the epilogue and the store warps
+constexpr int kBuilders = 4;
+constexpr int kEpiWarpsP = 16;
+constexpr int kThreadsP = 32 * (4 + 1 + 1 + kBuilders + kEpiWarpsP);
+constexpr int kBarsP = 1 + 2 + 2 + kQuads + kQuads + kSlotsP + kSlotsP + kRingP + kRingP;
+
+// debug build: cycles a role of CTA 0 spends in each of its waits (SPK_STEM_TRACE=1), printed when the kernel ends
+#ifdef SPK_DEBUG_SWITCHES
+#define STEMP_TIMED(acc, stmt) do { const long long _t0 = clock64(); stmt; acc += clock64() - _t0; } while (0)
+#else
+#define STEMP_TIMED(acc, stmt) do { stmt; } while (0)
+#endif
+
+struct StemPParams {
+  int trace;
+  const uint4* w;     // as StemTParams
+  const float* bias;  // [64]
+  __nv_bfloat16* y;   // [n, hp, wp, ldy]
+  int n, th, tw, hc, wc, hp, wp, ldy;
+  int bands, units;   // units = n * bands
+  int ncols, e_pitch, ring_pitch;
+  unsigned long long* stamp;
+};
+
+__global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_constant__ CUtensorMap map_x, const StemPParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 127u) & ~127u;
+  unsigned char* gbase = smem_raw + (base - raw);
+  // layout: E ring | W | two u8 strips | conv-row ring | barriers | tmem slot
+  const uint32_t e_off = 0, w_off = (uint32_t)(4 * kQuads * p.e_pitch), strip_off = w_off + kWBytes;
+  const uint32_t ring_off = strip_off + 2u * kStripRowsP * 256u, bar_off = ring_off + (uint32_t)(kRingP * p.ring_pitch);
+  int bi = 0;
+  const uint32_t bar0 = base + bar_off;
+  const uint32_t w_bar = bar0 + 8u * bi; bi += 1;
+  const uint32_t strip_full0 = bar0 + 8u * bi; bi += 2;
+  const uint32_t strip_empty0 = bar0 + 8u * bi; bi += 2;
+  const uint32_t quad_full0 = bar0 + 8u * bi; bi += kQuads;
+  const uint32_t quad_empty0 = bar0 + 8u * bi; bi += kQuads;
+  const uint32_t t_full0 = bar0 + 8u * bi; bi += kSlotsP;
+  const uint32_t t_empty0 = bar0 + 8u * bi; bi += kSlotsP;
+  const uint32_t ring_full0 = bar0 + 8u * bi; bi += kRingP;
+  const uint32_t ring_empty0 = bar0 + 8u * bi; bi += kRingP;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + bar_off + 8 * kBarsP);
+  const uint32_t ring_s = base + ring_off;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  pdl_trigger();
+  stamp_begin(p.stamp);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(w_bar, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(strip_full0 + 8u * s, 1);
+        mbar_init(strip_empty0 + 8u * s, kBuilders);
+      }
+      for (int s = 0; s < kQuads; ++s) {
+        mbar_init(quad_full0 + 8u * s, kBuilders);
+        mbar_init(quad_empty0 + 8u * s, 1);
+      }
+      for (int s = 0; s < kSlotsP; ++s) {
+        mbar_init(t_full0 + 8u * s, 1);
+        mbar_init(t_empty0 + 8u * s, kEpiWarpsP / 2);
+      }
+      for (int s = 0; s < kRingP; ++s) {
+        mbar_init(ring_full0 + 8u * s, 4);
+        mbar_init(ring_empty0 + 8u * s, 4);
+      }
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32((const void*)tmem_slot), kSlotsP * 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> image, pooled rows [p0, p1], first conv row, conv rows, accumulators, input row of E row 0
+  struct Unit { int image, p0, p1, c_lo, n_rows, nacc, y_base; };
+  auto unit_geom = [&](int unit) {
+    Unit u;
+    u.image = unit / p.bands;
+    u.p0 = (unit - u.image * p.bands) * kBand;
+    u.p1 = min(u.p0 + kBand, p.hp) - 1;
+    u.c_lo = max(0, 2 * u.p0 - 1);
+    const int c_hi = min(p.hc - 1, 2 * u.p1 + 1);
+    u.n_rows = c_hi - u.c_lo + 1;
+    u.nacc = (u.n_rows + 1) >> 1;
+    u.y_base = 2 * u.c_lo - 3;
+    return u;
+  };
+
+  if (warp == 5) {
+    // ===== producer =====
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, (uint32_t)kWBytes);
+      bulk_load(base + w_off, p.w, kWBytes, w_bar);
+      pdl_wait();  // the image planes are the previous kernel's output
+      int i = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++i) {
+        const Unit u = unit_geom(unit);
+        const int b = i & 1;
+        if (i >= 2) mbar_wait(strip_empty0 + 8u * b, (uint32_t)(((i >> 1) - 1) & 1));
+        mbar_expect_tx(strip_full0 + 8u * b, (uint32_t)(kStripRowsP * 256));
+        // pixel x of input row y lands at strip[(y - y_base) * 256 + x + kXOff]; out-of-image rows / columns are zero-filled
+        tma_load_3d(base + strip_off + (uint32_t)b * (kStripRowsP * 256), &map_x, strip_full0 + 8u * b, -kXOff, u.y_base, u.image);
+      }
+    }
+  } else if (warp >= 6 && warp < 6 + kBuilders) {
+    // ===== builders: E[j] = fp16 of pixels 2j-3 .. 2j+4 = strip bytes [2j + 13, 2j + 21) of the row =====
+    const int b = warp - 6;
+    int i = 0, qg = 0;
+    long long w_strip = 0, w_quad = 0;
+    const long long t_begin = clock64();
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++i) {
+      const Unit u = unit_geom(unit);
+      const int nq = u.nacc + 2;
+      STEMP_TIMED(w_strip, mbar_wait(strip_full0 + 8u * (i & 1), (uint32_t)((i >> 1) & 1)));
+      const unsigned char* strip = gbase + strip_off + (size_t)(i & 1) * (kStripRowsP * 256);
+      for (int q = 0; q < nq; ++q) {
+        const int g = qg + q, slot = g & (kQuads - 1);
+        if (g >= kQuads) STEMP_TIMED(w_quad, mbar_wait(quad_empty0 + 8u * slot, (uint32_t)(((g / kQuads) - 1) & 1)));
+        const uint32_t* srow = reinterpret_cast<const uint32_t*>(strip + (4 * q + b) * 256);
+        unsigned char* erow = gbase + e_off + (size_t)(slot * 4 + b) * p.e_pitch;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = lane + 32 * c;
+          if (j < p.wc) {
+            const int a = 2 * j + 13, wi = a >> 2;
+            const uint32_t sh = (uint32_t)(a & 3) * 8u;
+            const uint32_t w0 = srow[wi], w1 = srow[wi + 1], w2 = srow[wi + 2];
+            const uint2 c0 = bytes4_to_f16x4(__funnelshift_r(w0, w1, sh)), c1 = bytes4_to_f16x4(__funnelshift_r(w1, w2, sh));
+            *reinterpret_cast<uint4*>(erow + j * 16) = make_uint4(c0.x, c0.y, c1.x, c1.y);
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(quad_full0 + 8u * slot);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(strip_empty0 + 8u * (i & 1));
+      qg += nq;
+    }
+#ifdef SPK_DEBUG_SWITCHES
+    if (p.trace && blockIdx.x == 0 && b == 0 && lane == 0)
+      printf("stem_p builder: total %lld cycles, %d quads; waiting strip_full %lld, quad_empty %lld\n", clock64() - t_begin, qg, w_strip, w_quad);
+#endif
+    (void)t_begin; (void)w_strip; (void)w_quad;
+  } else if (warp == 4) {
+    // ===== MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues =====
+    mbar_wait(w_bar, 0);
+    const uint32_t w_s = base + w_off, e_s = base + e_off;
+    const uint32_t idesc = idesc_f16(128, p.ncols);
+    int qg = 0, tg = 0, qseen = 0;
+    long long w_qfull = 0, w_tempty = 0;
+    const long long t_begin = clock64();
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const Unit u = unit_geom(unit);
+      for (int t = 0; t < u.nacc; ++t, ++tg) {
+        for (; qseen < qg + t + 3; ++qseen)
+          STEMP_TIMED(w_qfull, mbar_wait(quad_full0 + 8u * (qseen & (kQuads - 1)), (uint32_t)((qseen / kQuads) & 1)));
+        const int slot = tg & (kSlotsP - 1);
+        if (tg >= kSlotsP) STEMP_TIMED(w_tempty, mbar_wait(t_empty0 + 8u * slot, (uint32_t)(((tg / kSlotsP) - 1) & 1)));
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(slot * 128);
+#pragma unroll
+        for (int m = 0; m < kWChunks / 2; ++m) {  // K chunks 2m, 2m + 1 = E rows 4t + 2m, + 1 of the unit (never split by the ring's wrap)
+          const uint32_t rr = (uint32_t)((((qg + t) << 2) + 2 * m) & (4 * kQuads - 1));
+          tc_mma_w(d, smem_desc_interleaved(w_s + (uint32_t)m * 4096u, 2048, 128),
+                   smem_desc_interleaved(e_s + rr * (uint32_t)p.e_pitch, (uint32_t)p.e_pitch, 128), idesc, m != 0 ? 1u : 0u);
+        }
+        tc_commit_w(t_full0 + 8u * slot);
+        tc_commit_w(quad_empty0 + 8u * ((qg + t) & (kQuads - 1)));  // quad t is not read by later accumulators
+      }
+      // the two trailing quads of the unit
+      tc_commit_w(quad_empty0 + 8u * ((qg + u.nacc) & (kQuads - 1)));
+      tc_commit_w(quad_empty0 + 8u * ((qg + u.nacc + 1) & (kQuads - 1)));
+      qg += u.nacc + 2;
+    }
+#ifdef SPK_DEBUG_SWITCHES
+    if (p.trace && blockIdx.x == 0 && lane == 0)
+      printf("stem_p mma: total %lld cycles, %d accumulators; waiting quad_full %lld, t_empty %lld\n", clock64() - t_begin, tg, w_qfull, w_tempty);
+#endif
+    (void)t_begin; (void)w_qfull; (void)w_tempty;
+  } else if (warp >= 6 + kBuilders) {
+    // ===== epilogue: group g takes the accumulators with (running index & 1) == g =====
+    const int e = warp - (6 + kBuilders);
+    const int grp = e >> 3;
+    const int half = (e >> 2) & 1;     // which part of the columns
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int rowsel = q >> 1;         // conv row of the accumulator's pair
+    const int ch = (q & 1) * 32 + lane;
+    const float bias = __ldg(p.bias + ch);
+    const float scale = __ldg(reinterpret_cast<const float*>(p.w) + kWBytes / 4 + ch);
+    const int np = p.ncols >> 4;  // 16-column pieces
+    const int kh = (np + 1) >> 1;
+    const int k0 = half ? kh : 0, k1 = half ? np : kh;
+    int tg0 = 0, rg0 = 0;
+    long long w_tfull = 0, w_rempty = 0;
+    const long long t_begin = clock64();
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const Unit u = unit_geom(unit);
+      for (int t = 0; t < u.nacc; ++t) {
+        const int tg = tg0 + t;
+        if ((tg & 1) != grp) continue;
+        const int slot = tg & (kSlotsP - 1);
+        const int idx = 2 * t + rowsel;
+        const bool row_ok = idx < u.n_rows;
+        const int rg = rg0 + idx, rs = rg & (kRingP - 1);
+        __syncwarp();  // tcgen05.ld below is warp-collective
+        STEMP_TIMED(w_tfull, mbar_wait(t_full0 + 8u * slot, (uint32_t)((tg / kSlotsP) & 1)));
+        tc_fence_after();
+        // the ring row's previous occupant (conv row rg - kRingP) has been consumed by the store warps
+        if (row_ok && rg >= kRingP) STEMP_TIMED(w_rempty, mbar_wait(ring_empty0 + 8u * rs, (uint32_t)(((rg / kRingP) - 1) & 1)));
+        const uint32_t hrow = ring_s + (uint32_t)(rs * p.ring_pitch + ch * 2);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
+        float carry = -INFINITY;  // conv column 16k - 1
+        auto piece = [&](const uint32_t (&v)[16], float cr, int k) {
+          const uint32_t hp_ = hrow + (uint32_t)((8 * k) * 128);
+          if (16 * k + 16 <= p.wc) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const float l0 = j == 0 ? cr : __uint_as_float(v[2 * j - 1]);
+              const float m0 = fmaxf(fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), l0);
+              const float m1 = fmaxf(fmaxf(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3])), __uint_as_float(v[2 * j + 1]));
+              const uint32_t o = relu_bf16x2(fmaf(m0, scale, bias), fmaf(m1, scale, bias));
+              sts_u16(hp_ + j * 128, o);
+              sts_u16(hp_ + (j + 1) * 128, o >> 16);
+            }
+          } else {  // the piece that holds the last conv column
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int pw = 8 * k + j;
+              if (pw < p.wp) {
+                float m = __uint_as_float(v[2 * j]);
+                if (2 * pw + 1 < p.wc) m = fmaxf(m, __uint_as_float(v[2 * j + 1]));
+                m = fmaxf(m, j == 0 ? cr : __uint_as_float(v[2 * j - 1]));
+                sts_u16(hp_ + j * 128, relu_bf16x2(fmaf(m, scale, bias), 0.f));
+              }
+            }
+          }
+        };
+        auto release = [&]() {  // this warp has read its part of the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty0 + 8u * slot);
+        };
+        uint32_t va[16], vb[16];
+        if (k0 < k1) {
+          if (k0 > 0) carry = tmem_ld1(taddr + (uint32_t)(16 * k0 - 1));
+          tmem_ld16(taddr + (uint32_t)(16 * k0), va);
+        }
+        for (int k = k0; k < k1; k += 2) {
+          tmem_ld_wait();  // piece k (and, the first time, the carry)
+          const bool more1 = k + 1 < k1;
+          if (more1)
+            tmem_ld16(taddr + (uint32_t)(16 * (k + 1)), vb);
+          else
+            release();
+          if (row_ok) piece(va, carry, k);
+          carry = __uint_as_float(va[15]);
+          if (more1) {
+            tmem_ld_wait();  // piece k + 1
+            if (k + 2 < k1)
+              tmem_ld16(taddr + (uint32_t)(16 * (k + 2)), va);
+            else
+              release();
+            if (row_ok) piece(vb, carry, k + 1);
+            carry = __uint_as_float(vb[15]);
+          }
+        }
+        if (k0 >= k1) release();  // (a row of at most 16 conv columns: the second warp of the quarter only keeps the barrier counts)
+        if (row_ok) {  // this warp's part of conv row idx is in the ring
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ring_full0 + 8u * rs);
+        }
+      }
+      tg0 += u.nacc;
+      rg0 += u.n_rows;
+    }
+#ifdef SPK_DEBUG_SWITCHES
+    if (p.trace && blockIdx.x == 0 && e == 0 && lane == 0)
+      printf("stem_p epilogue: total %lld cycles; waiting t_full %lld, ring_empty %lld\n", clock64() - t_begin, w_tfull, w_rempty);
+#endif
+    (void)t_begin; (void)w_tfull; (void)w_rempty;
+  } else {
+    // ===== store warps (0-3): per pooled row the vertical max of its three conv rows, coalesced NHWC stores =====
+    pdl_wait();  // (the output buffer may still be read by the previous step's kernels)
+    int rg0 = 0;
+    long long w_rfull = 0;
+    const long long t_begin = clock64();
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const Unit u = unit_geom(unit);
+      auto rfull = [&](int idx) {
+        const int rg = rg0 + idx;
+        STEMP_TIMED(w_rfull, mbar_wait(ring_full0 + 8u * (rg & (kRingP - 1)), (uint32_t)((rg / kRingP) & 1)));
+      };
+      auto raddr = [&](int idx) { return ring_s + (uint32_t)(((rg0 + idx) & (kRingP - 1)) * p.ring_pitch); };
+      int released = 0;  // unit-relative conv rows below this one have been handed back
+      for (int prow = u.p0; prow <= u.p1; ++prow) {
+        const int r1 = 2 * prow;
+        const bool has0 = r1 - 1 >= 0, has2 = r1 + 1 <= p.hc - 1;
+        const int i1 = r1 - u.c_lo;
+        if (has0) rfull(i1 - 1);
+        rfull(i1);
+        if (has2) rfull(i1 + 1);
+        const uint32_t b1 = raddr(i1);
+        const uint32_t b0 = has0 ? raddr(i1 - 1) : b1;  // (a missing row reads the middle one again)
+        const uint32_t b2 = has2 ? raddr(i1 + 1) : b1;
+        __nv_bfloat16* yrow = p.y + ((size_t)u.image * p.hp + prow) * p.wp * p.ldy;
+        for (int o = tid; o < p.wp * 8; o += 128) {
+          const int pw = o >> 3, j = o & 7;
+          const uint32_t off = (uint32_t)o * 16u;  // = pw * 128 + j * 16
+          uint4 m4 = lds_v4(b1 + off);
+          const uint4 t0 = lds_v4(b0 + off), t2 = lds_v4(b2 + off);
+          __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m4);
+          const __nv_bfloat162* q0 = reinterpret_cast<const __nv_bfloat162*>(&t0);
+          const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&t2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) mm[e] = __hmax2(__hmax2(mm[e], q0[e]), q2[e]);
+          *reinterpret_cast<uint4*>(yrow + (size_t)pw * p.ldy + j * 8) = m4;
+        }
+        // conv rows up to 2 prow are done with (2 prow + 1 also feeds the next pooled row)
+        __syncwarp();
+        for (; released <= i1; ++released)
+          if (lane == 0) mbar_arrive(ring_empty0 + 8u * ((rg0 + released) & (kRingP - 1)));
+      }
+      __syncwarp();
+      for (; released < u.n_rows; ++released)  // the unit's last odd conv row
+        if (lane == 0) mbar_arrive(ring_empty0 + 8u * ((rg0 + released) & (kRingP - 1)));
+      rg0 += u.n_rows;
+    }
+#ifdef SPK_DEBUG_SWITCHES
+    if (p.trace && blockIdx.x == 0 && tid == 0) printf("stem_p store: total %lld cycles; waiting ring_full %lld\n", clock64() - t_begin, w_rfull);
+#endif
+    (void)t_begin; (void)w_rfull;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  stamp_end(p.stamp);
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kSlotsP * 128);
+  }
+}
+
 }  // namespace
 
 bool stem_pool_t_supported(int wc, int wp) { return wc >= 2 && wc <= 128 && wp >= 1 && wp <= 64; }
@@ -459,12 +834,15 @@ int launch_stem_pool_t(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, co
   p.ring_pitch = wp * 128;
   p.rb_bytes = (kERows * p.rb_pitch + 127) / 128 * 128;
   p.region = (std::max(kRing * p.ring_pitch, p.rb_bytes + kERows * p.pitch) + 127) / 128 * 128;
-  // the tensor map of the u8 batch {tw, th, n}, box {256, kERows, 1}: cached per (pointer, geometry)
-  static thread_local struct { const void* x; int n, th, tw; CUtensorMap map; } cache = {nullptr, 0, 0, 0, {}};
-  if (p.use_tma && (cache.x != x || cache.n < n || cache.th != th || cache.tw != tw)) {
+  // the tensor map of the u8 batch {tw, th, n}, box {256, rows, 1}: cached per (pointer, geometry)
+  static const bool no_persistent = debug_env("SPK_STEM_STRIPS") != nullptr;  // A/B switch: the CTA-per-strip kernel
+  const bool persistent = p.use_tma && !no_persistent;
+  const int box_rows = persistent ? kStripRowsP : kERows;
+  static thread_local struct { const void* x; int n, th, tw, rows; CUtensorMap map; } cache = {nullptr, 0, 0, 0, 0, {}};
+  if (p.use_tma && (cache.x != x || cache.n < n || cache.th != th || cache.tw != tw || cache.rows != box_rows)) {
     cuuint64_t dims[3] = {(cuuint64_t)tw, (cuuint64_t)th, (cuuint64_t)n};
     cuuint64_t strides[2] = {(cuuint64_t)tw, (cuuint64_t)tw * th};
-    cuuint32_t box[3] = {256u, (cuuint32_t)kERows, 1u};
+    cuuint32_t box[3] = {256u, (cuuint32_t)box_rows, 1u};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = encode_fn()(&cache.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(x), dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -474,6 +852,37 @@ int launch_stem_pool_t(spk_ctx* ctx, int n, int th, int tw, const uint8_t* x, co
     cache.n = n;
     cache.th = th;
     cache.tw = tw;
+    cache.rows = box_rows;
+  }
+  if (persistent) {
+    StemPParams q;
+    static int trace_left = debug_env("SPK_STEM_TRACE") ? 3 : 0;
+    q.trace = trace_left > 0 ? 1 : 0;
+    if (trace_left > 0) --trace_left;
+    q.w = w;
+    q.bias = bias;
+    q.y = y;
+    q.n = n;
+    q.th = th;
+    q.tw = tw;
+    q.hc = hc;
+    q.wc = wc;
+    q.hp = hp;
+    q.wp = wp;
+    q.ldy = ldy;
+    q.bands = (hp + kBand - 1) / kBand;
+    q.units = n * q.bands;
+    q.ncols = p.ncols;
+    q.e_pitch = p.e_pitch;
+    q.ring_pitch = p.ring_pitch;
+    q.stamp = ctx->cur_stamp;
+    const size_t smem_p = 128 + (size_t)4 * kQuads * q.e_pitch + kWBytes + 2 * (size_t)kStripRowsP * 256 + (size_t)kRingP * q.ring_pitch +
+                          8 * kBarsP + 16;
+    SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    const int grid = std::min(q.units, ctx->sm_count);
+    SPK_CUDA_OK(ctx, launch_pdl(stem_pool_p_kernel, dim3((unsigned)grid), dim3(kThreadsP), smem_p, ctx->stream, cache.map, q));
+    SPK_LAUNCH_CHECK(ctx);
+    return SPK_OK;
   }
   const size_t smem = 128 + (size_t)kERows * p.e_pitch + kWBytes + (size_t)p.region + 8 * (kEGroups + 2 * kSlots + 3 + 2 * kRing) + 16;
   SPK_CUDA_OK(ctx, cudaFuncSetAttribute(stem_pool_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -133,7 +133,7 @@ def test_tcgen05_conv_matches_cuda_cores_and_torch(ctx, t, n, c1, c2, k, stride,
     assert float(np.abs(y_simt - y_tc).max()) <= 3e-2 * scale
 
 
-@pytest.mark.parametrize("t,n", [(224, 5), (180, 3), (64, 9), (90, 2), (256, 2), (30, 4)], ids=lambda v: str(v))
+@pytest.mark.parametrize("t,n", [(224, 5), (180, 3), (64, 9), (90, 2), (256, 2), (30, 4), (224, 300), (96, 200), (176, 160)], ids=lambda v: str(v))
 def test_fused_stem_matches_unfused_and_torch(ctx, t, n):
     """conv 7x7/2 (3 equal planes folded to 1) + BN + ReLU + max-pool 3x3/2: the fused tcgen05 kernel
     against the unfused CUDA-core path and a torch fp32 reference of the same ops."""

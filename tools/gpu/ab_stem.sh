@@ -1,9 +1,15 @@
 #!/bin/bash
-# A/B at STEP level, alternating in one call on one box: the transposed stem (default) against the old two-pass kernel
+# debug build: the persistent stem (stem_pool_p_kernel) against the CTA-per-strip kernel (SPK_STEM_STRIPS=1): parity, then steps
 mkdir -p gpurun_out
-for i in 1 2 3; do
-  for v in t hilo; do
-    SPK_STEM=$v timeout 300 python bench.py --steps 200 --warmup 10 --no-cpu-baseline 2>/dev/null | tail -1 | \
-      python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$v', round(d['value']), round(d['e2e']['value']), round(d['ms_per_step'],4), d['clocks'])"
-  done
+timeout 600 python -m pytest tests/test_gpu_conv.py -q -m gpu -x -k "stem" 2>&1 | tail -4 | cut -c1-300
+timeout 900 python -m pytest tests/test_gpu_network.py tests/test_gpu_bench_parity.py -q -m gpu -x -k "bf16" 2>&1 | tail -4 | cut -c1-300
+for v in p strips p strips; do
+  if [ $v == strips ]; then export SPK_STEM_STRIPS=1; else unset SPK_STEM_STRIPS; fi
+  timeout 600 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --e2e-bins 4 --profile-detail gpurun_out/pd_stem_$v.tsv > gpurun_out/bench_stem_$v.log 2> gpurun_out/bench_stem_$v.err; echo "bench $v rc=$?"
+  tail -c 300 gpurun_out/bench_stem_$v.err
+  python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_stem_$v.log').read().strip().splitlines()[-1])
+print('$v', round(d['value']), 'ms', round(d['ms_per_step'],4), 'frac', round(d['roofline']['frac'],3), d['kernel_ms_per_step'], d['parity']['max_dp'], d['clocks'])
+PY
 done
