@@ -426,7 +426,9 @@ constexpr int kSlotsP = 4;                     // TMEM accumulator ring (4 x 128
 constexpr int kRingP = 8;                      // conv rows between the epilogue and the store warps
 constexpr int kBuilders = 4;
 constexpr int kEpiWarpsP = 16;
-constexpr int kThreadsP = 32 * (4 + 1 + 1 + kBuilders + kEpiWarpsP);
+constexpr int kStoreWarps = 4;  // (8 measured slower: 0.115 vs 0.096 ms -- more warps contending for issue slots and the TMEM read pipe)
+constexpr int kMmaWarp = kStoreWarps, kProdWarp = kStoreWarps + 1, kBuild0 = kStoreWarps + 2, kEpi0 = kBuild0 + kBuilders;
+constexpr int kThreadsP = 32 * (kStoreWarps + 1 + 1 + kBuilders + kEpiWarpsP);
 constexpr int kBarsP = 1 + 2 + 2 + kQuads + kQuads + kSlotsP + kSlotsP + kRingP + kRingP;
 
 // debug build: cycles a role of CTA 0 spends in each of its waits (SPK_STEM_TRACE=1), printed when the kernel ends
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
   pdl_trigger();
   stamp_begin(p.stamp);
 
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       mbar_init(w_bar, 1);
       for (int s = 0; s < 2; ++s) {
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
       }
       for (int s = 0; s < kRingP; ++s) {
         mbar_init(ring_full0 + 8u * s, 4);
-        mbar_init(ring_empty0 + 8u * s, 4);
+        mbar_init(ring_empty0 + 8u * s, kStoreWarps);
       }
       mbar_init_fence();
     }
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
     return u;
   };
 
-  if (warp == 5) {
+  if (warp == kProdWarp) {
     // ===== producer =====
     if (lane == 0) {
       mbar_expect_tx(w_bar, (uint32_t)kWBytes);
@@ -534,9 +536,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
         tma_load_3d(base + strip_off + (uint32_t)b * (kStripRowsP * 256), &map_x, strip_full0 + 8u * b, -kXOff, u.y_base, u.image);
       }
     }
-  } else if (warp >= 6 && warp < 6 + kBuilders) {
+  } else if (warp >= kBuild0 && warp < kBuild0 + kBuilders) {
     // ===== builders: E[j] = fp16 of pixels 2j-3 .. 2j+4 = strip bytes [2j + 13, 2j + 21) of the row =====
-    const int b = warp - 6;
+    const int b = warp - kBuild0;
     int i = 0, qg = 0;
     long long w_strip = 0, w_quad = 0;
     const long long t_begin = clock64();
@@ -574,7 +576,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
       printf("stem_p builder: total %lld cycles, %d quads; waiting strip_full %lld, quad_empty %lld\n", clock64() - t_begin, qg, w_strip, w_quad);
 #endif
     (void)t_begin; (void)w_strip; (void)w_quad;
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues =====
     mbar_wait(w_bar, 0);
     const uint32_t w_s = base + w_off, e_s = base + e_off;
@@ -610,9 +612,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
       printf("stem_p mma: total %lld cycles, %d accumulators; waiting quad_full %lld, t_empty %lld\n", clock64() - t_begin, tg, w_qfull, w_tempty);
 #endif
     (void)t_begin; (void)w_qfull; (void)w_tempty;
-  } else if (warp >= 6 + kBuilders) {
+  } else if (warp >= kEpi0) {
     // ===== epilogue: group g takes the accumulators with (running index & 1) == g =====
-    const int e = warp - (6 + kBuilders);
+    const int e = warp - kEpi0;
     const int grp = e >> 3;
     const int half = (e >> 2) & 1;     // which part of the columns
     const int q = warp & 3;            // TMEM lane quarter this warp may read
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
 #endif
     (void)t_begin; (void)w_tfull; (void)w_rempty;
   } else {
-    // ===== store warps (0-3): per pooled row the vertical max of its three conv rows, coalesced NHWC stores =====
+    // ===== store warps (0 .. kStoreWarps - 1): per pooled row the vertical max of its three conv rows, coalesced NHWC stores =====
     pdl_wait();  // (the output buffer may still be read by the previous step's kernels)
     int rg0 = 0;
     long long w_rfull = 0;
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
         const uint32_t b0 = has0 ? raddr(i1 - 1) : b1;  // (a missing row reads the middle one again)
         const uint32_t b2 = has2 ? raddr(i1 + 1) : b1;
         __nv_bfloat16* yrow = p.y + ((size_t)u.image * p.hp + prow) * p.wp * p.ldy;
-        for (int o = tid; o < p.wp * 8; o += 128) {
+        for (int o = tid; o < p.wp * 8; o += 32 * kStoreWarps) {
           const int pw = o >> 3, j = o & 7;
           const uint32_t off = (uint32_t)o * 16u;  // = pw * 128 + j * 16
           uint4 m4 = lds_v4(b1 + off);
@@ -767,7 +769,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) stem_pool_p_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   stamp_end(p.stamp);
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kSlotsP * 128);
   }
