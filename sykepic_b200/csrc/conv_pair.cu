@@ -43,6 +43,7 @@ constexpr int kMaxTaps = 9;
 constexpr int kABytes = 128 * kBK * 2;
 constexpr int kIoSlot = 128 * 128;  // one 128-pixel x 64-channel slab
 constexpr int kMaxStages = 8;
+constexpr int kMaxResSlots = 4;  // residual slabs in flight per CTA (64-channel slabs of 16 KB)
 constexpr size_t kSmemMax = 232448;
 
 struct alignas(64) PairParams {
@@ -81,17 +82,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gen = smem_raw + (base - raw);
   const uint32_t res_off = (uint32_t)p.stages * kStageBytes;
-  const uint32_t out_off = res_off + (p.res_slots ? 2u * kIoSlot : 0u);  // no residual ring when the layer has none
+  const uint32_t out_off = res_off + (uint32_t)p.res_slots * kIoSlot;  // no residual ring when the layer has none
   const uint32_t bias_off = out_off + 2u * kIoSlot;
   const uint32_t bar0 = base + ((bias_off + (uint32_t)p.cout * 4u + 15u) & ~15u);
   float* bias_sm = reinterpret_cast<float*>(gen + bias_off);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
   auto r_full = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
-  auto r_empty = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 2 + s); };
-  auto t_full = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 4 + s); };
-  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 6 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 8 * (2 * kMaxStages + 8));
+  auto r_empty = [&](int s) { return bar0 + 8u * (2 * kMaxStages + kMaxResSlots + s); };
+  auto t_full = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 2 * kMaxResSlots + s); };
+  auto t_empty = [&](int s) { return bar0 + 8u * (2 * kMaxStages + 2 * kMaxResSlots + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (bar0 - base) + 8 * (2 * kMaxStages + 2 * kMaxResSlots + 4));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -106,9 +107,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
       mbar_init(full_bar(s), 1);   // used in the leader only: its producer's arrive.expect_tx
       mbar_init(empty_bar(s), 1);  // multicast tcgen05.commit
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxResSlots; ++s) {
       mbar_init(r_full(s), 1);
       mbar_init(r_empty(s), kEpiWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(t_full(s), 1);               // multicast tcgen05.commit
       mbar_init(t_empty(s), 2 * kEpiWarps);  // used in the leader only: the epilogue warps of both CTAs
     }
@@ -230,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
           mbar_wait(r_empty(rs), rph ^ 1u);
           mbar_expect_tx(r_full(rs), (uint32_t)kIoSlot);
           tma_load_4d(base + res_off + (uint32_t)rs * kIoSlot, &p.map_res, r_full(rs), nt * BN + slab * 64, w0, h0, n0);
-          if (++rs == 2) {
+          if (++rs == p.res_slots) {
             rs = 0;
             rph ^= 1u;
           }
@@ -323,7 +326,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_pa
         if (with_res) {
           __syncwarp();
           if (lane == 0) mbar_arrive(r_empty(rs));
-          if (++rs == 2) {
+          if (++rs == p.res_slots) {
             rs = 0;
             rph ^= 1u;
           }
@@ -460,8 +463,12 @@ int pair_conv_plan_create(spk_ctx* ctx, const ConvGeom& g_max, const float* w, c
 
   // ---- shared memory: stages under the budget
   const size_t stage = (size_t)kABytes + (size_t)(p->bn / 2) * kBK * 2 * (p->ds ? 2 : 1);
-  prm.res_slots = g.ldres ? 2 : 0;
-  const size_t fixed = 1024 + (size_t)(2 + prm.res_slots) * kIoSlot + (size_t)g.cout * 4 + 16 + 8 * (2 * kMaxStages + 8) + 16;
+  // residual ring: 4 slabs where the layer is HBM-bound by construction (a 1x1 expansion: a few k blocks of math per 64 KB of
+  // residual + 64 KB of output per tile; with 2 slabs = 32 KB in flight per SM the residual stream could not cover the
+  // HBM latency), 2 for the 3x3 layers (tensor-bound, the stages matter more)
+  static const char* rs_env = debug_env("SPK_PAIR_RES_SLOTS");  // A/B switch (debug build)
+  prm.res_slots = g.ldres ? (rs_env ? std::max(2, std::min(kMaxResSlots, atoi(rs_env))) : (g.kh * g.kw == 1 ? 4 : 2)) : 0;
+  const size_t fixed = 1024 + (size_t)(2 + prm.res_slots) * kIoSlot + (size_t)g.cout * 4 + 16 + 8 * (2 * kMaxStages + 2 * kMaxResSlots + 6) + 16;
   prm.stages = (int)std::min<size_t>(kMaxStages, (kSmemMax - fixed) / stage);
   if (prm.stages < 2) {
     delete p;
