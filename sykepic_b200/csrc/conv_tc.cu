@@ -57,6 +57,7 @@ struct alignas(64) TcParams {
   int tiles_w, tiles_h, tiles_img, tiles_n;
   int taps, kchunks, cin_pad;
   int total_tiles;
+  int st32;         // bf16 epilogue: the output rows allow 32-byte stores (pointer and channel stride multiples of 32 bytes)
   int split_chunk;  // kModeSplit: k blocks per accumulation chunk (kSplitChunk)
   const float* wscale;         // kModeSplit: 2^-k(o) per output channel, undoes the power-of-two scaling of the fp16 weights
   unsigned long long* faults;  // kModeSplit: counts tiles with an output beyond the fp16 range of the SplitF format
@@ -405,8 +406,12 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
           uint4* cp = reinterpret_cast<uint4*>(row + ((j ^ (r & 7)) << 4));
           uint4 q = *cp;
           __nv_bfloat162* b2 = reinterpret_cast<__nv_bfloat162*>(&q);
-          const float* sc = pre_tab + c0 + 8 * j;
-          const float* sh = pre_tab + 1024 + c0 + 8 * j;
+          // the chunk's 8 scales and 8 shifts as four 16-byte loads (all lanes of a warp read the same words: broadcasts; with
+          // sixteen 4-byte loads this line was 14 % of the kernel's samples)
+          const float4 s0 = *reinterpret_cast<const float4*>(pre_tab + c0 + 8 * j), s1 = *reinterpret_cast<const float4*>(pre_tab + c0 + 8 * j + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(pre_tab + 1024 + c0 + 8 * j), h1 = *reinterpret_cast<const float4*>(pre_tab + 1024 + c0 + 8 * j + 4);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 f = __bfloat1622float2(b2[e]);
@@ -486,18 +491,21 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
+            uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              o.x = *reinterpret_cast<uint32_t*>(&t0);
-              o.y = *reinterpret_cast<uint32_t*>(&t1);
-              o.z = *reinterpret_cast<uint32_t*>(&t2);
-              o.w = *reinterpret_cast<uint32_t*>(&t3);
-              *reinterpret_cast<uint4*>(yrow + c + j) = o;
+            for (int j = 0; j < 32; j += 2) {
+              const __nv_bfloat162 t = __floats2bfloat162_rn(f[j], f[j + 1]);
+              o[j >> 1] = *reinterpret_cast<const uint32_t*>(&t);
+            }
+            if (p.st32) {  // 256-bit stores: whole 32-byte sectors (16-byte stores at a pixel stride write every sector in two halves)
+#pragma unroll
+              for (int j = 0; j < 32; j += 16)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + c + j), "r"(o[j / 2]), "r"(o[j / 2 + 1]),
+                             "r"(o[j / 2 + 2]), "r"(o[j / 2 + 3]), "r"(o[j / 2 + 4]), "r"(o[j / 2 + 5]), "r"(o[j / 2 + 6]), "r"(o[j / 2 + 7])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(yrow + c + j) = make_uint4(o[j / 2], o[j / 2 + 1], o[j / 2 + 2], o[j / 2 + 3]);
             }
           }
           __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the predicated stores
@@ -937,6 +945,7 @@ int tc_conv_launch(spk_ctx* ctx, TcConvPlan* p, int n, const void* x, const void
   prm.n = n;
   prm.res = (const __nv_bfloat16*)res;
   prm.y = (__nv_bfloat16*)y;
+  prm.st32 = (((uintptr_t)y & 31) == 0 && p->g.ldy % 16 == 0 && (!y_ds || (((uintptr_t)y_ds & 31) == 0 && prm.ldy2 % 16 == 0))) ? 1 : 0;
   prm.y2 = (__nv_bfloat16*)y_ds;
   prm.stamp = ctx->cur_stamp;
   if (p->ds && !y_ds) return fail(ctx, SPK_ERR_INVALID, "tcgen05 convolution: fused downsample without an output");
