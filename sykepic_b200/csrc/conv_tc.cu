@@ -38,7 +38,9 @@ namespace {
 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
 constexpr int kBK = 64;           // channels per k block (128 bytes of bf16 = one swizzle row)
-constexpr int kThreads = 192;     // 6 warps
+constexpr int kEpiWarps = 8;      // two per TMEM lane quarter, each half of the tile's columns (one warp per quarter walked a
+                                  // 128-column tile in ~3600 cycles of dependent tcgen05.ld -> math -> store: the DenseNet 1x1 layers were epilogue-bound)
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA producer, MMA issuer, epilogue warps
 constexpr int kMaxTaps = 9;
 constexpr int kABytes = kBM * kBK * 2;
 
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), kEpiWarps);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&p.map_b);
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
         }
       }
     }
-  } else if (PRE && warp >= 6) {
+  } else if (PRE && warp >= 2 + kEpiWarps) {
     // ===== kModePre transform: 8 warps, thread -> (pixel row, four of its eight 16-byte channel chunks).  SWIZZLE_128B
     // puts logical chunk j of row r at physical chunk j ^ (r & 7).  Same arithmetic as the stand-alone affine_relu kernel
     // (fp32 fma, ReLU, round to bf16), so the fused result is bit-identical to the unfused one. =====
@@ -433,9 +435,14 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
         }
       }
     }
-  } else if (warp >= 2 && warp < 6) {
-    // ===== epilogue: 4 warps, warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+  } else if (warp >= 2 && warp < 2 + kEpiWarps) {
+    // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a quarter take half of the
+    // tile's columns each (BN = 32: the second one only keeps the barrier counts) =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int kHalfCols = BN >= 64 ? BN / 2 : BN;
+    const int c_lo = BN >= 64 ? half * kHalfCols : 0;
+    const bool works = BN >= 64 || half == 0;
     const int row = q * 32 + lane;  // pixel of the tile == TMEM lane
     const int wbi = row % p.wb;
     const int hbi = (row / p.wb) % p.hb;
@@ -460,7 +467,8 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
       // one pass over BN accumulator columns: + bias (+ residual) (ReLU) -> bf16 -> 16-byte stores of the pixel's row
       auto drain = [&](uint32_t taddr, const float* brow, const __nv_bfloat16* rrow, __nv_bfloat16* yrow, bool relu) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = c_lo; c < c_lo + kHalfCols; c += 32) {
+          if (!works) break;
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
           tmem_ld_wait();
@@ -517,22 +525,24 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
         const uint32_t* rrow = p.res ? reinterpret_cast<const uint32_t*>(p.res) + pix * p.ldres + nt * BN : nullptr;
         uint32_t* yrow = reinterpret_cast<uint32_t*>(p.y) + pix * p.ldy + nt * BN;
         const float* brow = p.bias + nt * BN;
-        float part[BN];
+        float part[kHalfCols];  // this warp's columns [c_lo, c_lo + kHalfCols)
 #pragma unroll
-        for (int c = 0; c < BN; ++c) part[c] = 0.f;
+        for (int c = 0; c < kHalfCols; ++c) part[c] = 0.f;
         const int nchunks = (kblocks + p.split_chunk - 1) / p.split_chunk;
         for (int ch = 0; ch < nchunks; ++ch) {
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::kAccCols);
+          if (works) {
 #pragma unroll
-          for (int c = 0; c < BN; c += 16) {
-            uint32_t v[16], vl[16];
-            tc::tmem_ld16(taddr + (uint32_t)c, v);
-            tc::tmem_ld16(taddr + (uint32_t)(BN + c), vl);
-            tmem_ld_wait();
+            for (int c = 0; c < kHalfCols; c += 16) {
+              uint32_t v[16], vl[16];
+              tc::tmem_ld16(taddr + (uint32_t)(c_lo + c), v);
+              tc::tmem_ld16(taddr + (uint32_t)(BN + c_lo + c), vl);
+              tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) part[c + j] += __uint_as_float(v[j]) + __uint_as_float(vl[j]);
+              for (int j = 0; j < 16; ++j) part[c + j] += __uint_as_float(v[j]) + __uint_as_float(vl[j]);
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -543,10 +553,13 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
           }
         }
         bool ovf = false;
-        if (valid) {
-          const float* srow = p.wscale + nt * BN;
+        if (valid && works) {
+          const float* srow = p.wscale + nt * BN + c_lo;
+          brow += c_lo;
+          yrow += c_lo;
+          if (rrow) rrow += c_lo;
 #pragma unroll
-          for (int c = 0; c < BN; c += 4) {
+          for (int c = 0; c < kHalfCols; c += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c));
             const float4 s4 = __ldg(reinterpret_cast<const float4*>(srow + c));  // powers of two: exact
             float f[4] = {fmaf(part[c], s4.x, b4.x), fmaf(part[c + 1], s4.y, b4.y), fmaf(part[c + 2], s4.z, b4.z), fmaf(part[c + 3], s4.w, b4.w)};
