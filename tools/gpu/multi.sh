@@ -1,5 +1,5 @@
 #!/bin/bash
-# multi-GPU pass (arg1 = N GPUs, arg2 = archive bins, default 1000): BASELINE configs 2-5 under torchrun, one rank per GPU
+# multi-GPU pass (arg1 = N GPUs, arg2 = archive bins, default 1000; 0 = skip the archive): BASELINE configs 2-5 under torchrun, one rank per GPU
 N=${1:-8}
 BINS=${2:-1000}
 mkdir -p gpurun_out
@@ -14,7 +14,7 @@ run r2_bench_r18_g$N $TR bench.py --gpus $N --steps 100 --warmup 5 --no-cpu-base
 run r2_bench_r50_g$N $TR bench.py --gpus $N --arch resnet50 --steps 30 --warmup 3 --no-cpu-baseline --e2e-bins 24
 run r2_bench_d121_g$N $TR bench.py --gpus $N --arch densenet121 --steps 30 --warmup 3 --no-cpu-baseline --e2e-bins 24
 df -h /dev/shm | tail -1
-run r2_archive_g$N $TR tools/archive_bench.py --bins $BINS
+[ "$BINS" != "0" ] && run r2_archive_g$N $TR tools/archive_bench.py --bins $BINS
 python - <<PY
 import json
 for f in ['r2_bench_r18_g$N','r2_bench_r50_g$N','r2_bench_d121_g$N','r2_archive_g$N']:
