@@ -89,3 +89,25 @@ def test_prob_call_hands_main_the_work_list(tmp_path, monkeypatch):
     assert seen["kw"]["samples_as_images"] is True
     probability.call(SimpleNamespace(**{**base, "images": [str(imgs / "B_IFCB1_00007.png"), str(imgs / "A_IFCB1_00002.png")]}))
     assert {k: [p.name for p in v] for k, v in seen["args"][0].items()} == {"A_IFCB1": ["A_IFCB1_00002.png"], "B_IFCB1": ["B_IFCB1_00007.png"]}
+
+
+def test_default_precision_is_fp32_accuracy_on_the_tensor_cores(monkeypatch):
+    """The reference computes in fp32 (compute/probability.py:189-194).  The CLI's default precision is the one that keeps the
+    1e-4 gate AND runs on tcgen05 ("fp32_tc"); `--precision` and SYKEPIC_PRECISION select the exact CUDA-core path or bf16."""
+    import importlib
+
+    from sykepic_b200.compute import probability
+
+    monkeypatch.delenv("SYKEPIC_PRECISION", raising=False)
+    importlib.reload(probability)
+    assert probability.DEFAULT_PRECISION == "fp32_tc"
+    p = build_parser()
+    assert p.parse_args(["prob", "-r", "R", "-m", "M", "-o", "O"]).precision is None  # -> DEFAULT_PRECISION
+    assert p.parse_args(["prob", "-r", "R", "-m", "M", "-o", "O", "--precision", "fp32"]).precision == "fp32"
+    with pytest.raises(SystemExit):
+        p.parse_args(["prob", "-r", "R", "-m", "M", "-o", "O", "--precision", "fp16"])
+    monkeypatch.setenv("SYKEPIC_PRECISION", "bf16")
+    importlib.reload(probability)
+    assert probability.DEFAULT_PRECISION == "bf16"
+    monkeypatch.delenv("SYKEPIC_PRECISION")
+    importlib.reload(probability)
