@@ -150,6 +150,9 @@ int spk_preprocess(spk_ctx* ctx, const uint8_t* roi_bytes, int64_t roi_len,
                    const int64_t* start, const int32_t* width, const int32_t* height, int64_t n,
                    int target_h, int target_w, int border_mode, int channels,
                    int out_dtype, int out_layout, const float* lut, void* out);
+/* The fault counter also counts, in SPK_PRECISION_FP32_TC, every tile of a convolution or of the stem whose output left the
+ * fp16 range of the split activation format (|x| > 65504: the value saturates); a caller must treat a forward pass after
+ * which the counter moved as invalid (sykepic_b200/engine.py raises ArithmeticError and points at --precision fp32). */
 int spk_fault_count(spk_ctx* ctx, int64_t* count);
 
 /* ---- A5/A6/A7: the network (kernels K2) -----------------------------------------------
