@@ -181,6 +181,36 @@ def test_cli_prob_then_class(model_dirs, tmp_path):
     assert lines[0].startswith("Time,") and len(lines) == 4
 
 
+@pytest.mark.parametrize("mode", ["thread", "process"])
+def test_prob_on_two_gpus_writes_the_same_files(model_dirs, tmp_path, monkeypatch, mode):
+    """`sykepic prob --gpus 2` (probability.main(devices=2): bins sharded by .roi size over the GPUs, one host thread or one
+    spawned process per GPU, no collective): every bin processed once, the CSV files byte-identical to the
+    one-GPU run.  Needs two GPUs (`gpurun --gpus 2`); skipped on a one-GPU box."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = "r18_180"
+    raw = tmp_path / "raw"
+    names = []
+    for rep in range(3):  # nine bins: the three of the case under three names each
+        for bname, b in case_bins(case):
+            name = bname[:-3] + f"{100 + rep:03d}"
+            synth.write_bin(raw, name, b)
+            names.append(name)
+    paths = sorted(p.with_suffix("") for p in raw.glob("*.roi"))
+    assert len(paths) == 9
+    one = probability.main(paths, model_dirs(case), tmp_path / "one", batch_size=64, progress_bar=False, precision="bf16", devices=1)
+    monkeypatch.setenv("SYKEPIC_MULTI", mode)
+    two = probability.main(paths, model_dirs(case), tmp_path / "two", batch_size=64, progress_bar=False, precision="bf16", devices=2)
+    assert set(one) == set(two) and len(two) == 9
+    a = sorted((tmp_path / "one").rglob("*.prob.csv"))
+    b = sorted((tmp_path / "two").rglob("*.prob.csv"))
+    assert [f.relative_to(tmp_path / "one") for f in a] == [f.relative_to(tmp_path / "two") for f in b] and len(a) == 9
+    for fa, fb in zip(a, b):
+        assert fa.read_bytes() == fb.read_bytes(), fa.name
+
+
 def test_image_mode_matches_raw_mode(engines, model_dirs, tmp_path):
     """SURVEY 8f rank 1, `sykepic prob --image-dir`: the ROIs of two bins written as `<sample>_<roi>.png` (what
     ifcb.raw_to_png produces, sykepic/utils/ifcb.py:76-118) go through `probability.call` and give the raw mode's
