@@ -229,6 +229,7 @@ struct Cfg {
   // both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
   // (kModeSplit: A = B = fp16, format 0)
   static constexpr uint32_t kIdesc = (1u << 4) | (MODE == kModeSplit ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  static constexpr uint32_t kIdescSplit2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);  // fp16 x fp16, N = 2 BN
 };
 
 template <int BN, int MODE>
@@ -350,17 +351,22 @@ __global__ void __launch_bounds__(MODE == kModePre ? kThreadsPre : kThreads, 1) 
           const uint32_t sa = base + stage * C::kStageBytes;
           const uint64_t a_desc = smem_desc_sw128(sa);
           const uint64_t b_desc = smem_desc_sw128(sa + kABytes);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (chunk_start && k == 0) ? 0u : 1u);
-          }
-          if (SPLIT) {  // the lo weights against the same (hi, lo) activation tile, into their own accumulator (these small
-                        // terms would double the number of truncating additions into the large sum)
-            const uint64_t b2_desc = smem_desc_sw128(sa + kABytes + C::kBBytes);
+          if constexpr (SPLIT) {
+            // ONE MMA of N = 2 BN per k step: the hi-weight tile and the lo-weight tile lie back to back in the stage (two TMA
+            // boxes of BN rows x 128 bytes, each a multiple of 1024 bytes: together a valid 2 BN-row SWIZZLE_128B tile), the
+            // accumulator columns [0, BN) get x * w_hi and [BN, 2 BN) get x * w_lo as before (own accumulator for the small
+            // terms: they would double the number of truncating additions into the large sum).  Against two N = BN MMAs the
+            // activation tile is read once instead of twice: the split mode was shared-memory bound (BN = 64: 12 KB of operand
+            // reads per 64 tensor cycles, now 8 KB)
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              tc_mma_w(d_tmem + (uint32_t)BN, a_desc + (uint64_t)(2 * k), b2_desc + (uint64_t)(2 * k), C::kIdesc, (chunk_start && k == 0) ? 0u : 1u);
+              tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdescSplit2, (chunk_start && k == 0) ? 0u : 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              tc_mma_w(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), C::kIdesc, (chunk_start && k == 0) ? 0u : 1u);
+            }
           }
           if (DS) {
             // the centre tap of a 3x3 / stride 2 / pad 1 filter samples exactly the pixels a 1x1 / stride 2
